@@ -1,0 +1,218 @@
+/*
+ * msg_b200.h -- C-ABI of the B200-native (sm_100a) multi-style GAN hot path.
+ *
+ * The reference (regicide211212/multi-style-transfer-gan) is 100 % Python and has no FFI layer
+ * (SURVEY.md 2.1); its "operator interface" for this path is the set of torch.nn library ops its
+ * modules dispatch.  Each entry point below names the reference call site (file:line, relative to
+ * the reference root) whose library op it replaces.  The Python drop-in classes in
+ * multi_style_transfer_gan_b200/ bind these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes, cudaStream_t passed as void*.
+ *   - every function returns 0 on success or a negative MSG_ERR_* code; msg_last_error() gives a
+ *     thread-local message.  No exceptions, no allocation, no ownership transfer: the caller owns
+ *     inputs, outputs and workspaces.
+ *   - activations are NHWC ("pixel-major, channel-contiguous"), dtype MSG_F32 or MSG_BF16; all
+ *     statistics, gradients of parameters and optimizer state are fp32.
+ *   - the library refuses to run on anything but compute capability 10.x (no fallback).
+ */
+#ifndef MSG_B200_H_
+#define MSG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSG_OK 0
+#define MSG_ERR_SHAPE (-1)
+#define MSG_ERR_ALIGN (-2)
+#define MSG_ERR_ARCH (-3)
+#define MSG_ERR_CUDA (-4)
+#define MSG_ERR_UNSUPPORTED (-5)
+
+#define MSG_F32 0
+#define MSG_BF16 1
+
+/* epilogue / elementwise activations */
+#define MSG_ACT_NONE 0
+#define MSG_ACT_RELU 1
+#define MSG_ACT_LRELU 2 /* LeakyReLU(0.2), enhanced_generator.py:238 */
+#define MSG_ACT_TANH 3  /* enhanced_generator.py:138 */
+
+/* msg_conv_desc.flags */
+#define MSG_CONV_STATS 1u      /* accumulate per-(n,cout) sum / sum-of-squares of the output   */
+#define MSG_CONV_OUT_NCHW_F32 2u /* write the result as fp32 NCHW (final image, Cout small)     */
+#define MSG_CONV_ACCUM 8u      /* y += result (sums the gradient branches of a fan-out)          */
+#define MSG_CONV_FORCE_SIMT 256u /* debugging: never take the tcgen05 path                      */
+#define MSG_CONV_IN_NORM 4u    /* normalise the INPUT on load with in_stats (IN + act fused
+                                   into the consumer's operand fetch)                             */
+
+/* weight packing modes for msg_pack_conv_weight */
+#define MSG_PACK_FWD 0        /* OIHW            -> [O][KH][KW][I]                                */
+#define MSG_PACK_DGRAD_S1 1   /* OIHW            -> [I][KH-1-kh][KW-1-kw][O]  (stride-1 dgrad)    */
+#define MSG_PACK_CONVT_PHASES 2 /* [I][O][4][4]  -> [4 phases][O][2][2][I]    (4x4 s2 p1 convT)   */
+
+const char* msg_last_error(void);
+int msg_version(void);
+/* 0 if the current device is sm_100 (B200); MSG_ERR_ARCH otherwise. */
+int msg_check_device(void);
+int msg_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic "gather convolution" (implicit GEMM).  One descriptor covers every conv on the path:
+ *   Conv2d 7x7 s1 p3 (enhanced_generator.py:92,137), Conv2d 4x4 s2 p1 (:99,106,237-249),
+ *   the 1x1 qkv/proj/branch1/fusion convs (:10,11,53,73), the dilated 3x3 branches (:58,63,68),
+ *   each sub-pixel phase of ConvTranspose2d 4x4 s2 p1 (:121,128), D heads (:256,262,265),
+ *   and, with re-packed weights, every dgrad of the above.
+ *
+ *   for (n, i, j) in [N, Hg, Wg], co in [0, Cout):
+ *     acc = bias[co] + sum_{th<KH, tw<KW, ci<Cin}
+ *             x[n, i*in_stride - pad_h + th*dil, j*in_stride - pad_w + tw*dil, ci_off + ci]   (0 outside)
+ *             * w[co][th][tw][ci]
+ *     y[n, i*out_stride + out_off_h, j*out_stride + out_off_w, co_off + co] = act(acc)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int dtype;                            /* MSG_F32 / MSG_BF16: x, w, y                          */
+  int N;
+  int Hi, Wi, Ci_total, ci_off, Cin;    /* input tensor [N,Hi,Wi,Ci_total], channel slice used  */
+  int Ho, Wo, Co_total, co_off, Cout;   /* output tensor [N,Ho,Wo,Co_total], slice written      */
+  int Hg, Wg;                           /* GEMM pixel grid                                      */
+  int KH, KW, in_stride, pad_h, pad_w, dil;
+  int out_stride, out_off_h, out_off_w;
+  int act;                              /* MSG_ACT_*                                            */
+  unsigned flags;                       /* MSG_CONV_*                                           */
+  int in_act;                           /* activation applied after the fused input norm        */
+} msg_conv_desc;
+
+/* x, w (packed [Cout][KH*KW*Cin], dtype), bias fp32 [Cout] or NULL, y, stats fp32 [N][Co_total][2]
+ * (only with MSG_CONV_STATS; must be zeroed by the caller; accumulates across calls),
+ * in_stats fp32 [N][Ci_total][2] raw sums of the input plane (only with MSG_CONV_IN_NORM). */
+int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+               float* stats, const float* in_stats, void* stream);
+
+/* wgrad of the same descriptor: dw[co][th][tw][ci] (fp32, packed layout, ACCUMULATED into) =
+ * sum over pixels of dy[..., co] * gathered x[..., ci].  Replaces autograd's conv weight grads for
+ * every conv above (enhanced_train.py:84,121). */
+int msg_conv2d_wgrad(const msg_conv_desc* d, const void* x, const void* dy, float* dw_packed,
+                     void* stream);
+
+/* fp32 master weight (PyTorch layout) -> packed operand of `dtype`.  O, I are the leading two dims
+ * of the source tensor as stored by PyTorch (Conv2d: O=Cout, I=Cin; ConvTranspose2d: O=Cin, I=Cout
+ * for MSG_PACK_CONVT_PHASES pass the tensor as stored, O=dim0, I=dim1).  `scale` (device fp32
+ * scalar or NULL) multiplies by 1/(*scale): spectral norm's weight_orig / sigma
+ * (enhanced_generator.py:269-271). */
+int msg_pack_conv_weight(const float* w, int dim0, int dim1, int KH, int KW, int mode, int dtype,
+                         const float* inv_scale_denominator, void* out, void* stream);
+/* inverse scatter of a packed fp32 gradient back to PyTorch layout (accumulates: dst += src). */
+int msg_unpack_conv_wgrad(const float* dw_packed, int dim0, int dim1, int KH, int KW, int mode,
+                          float* dw, void* stream);
+
+/* column sums: db[c] += sum over rows of dy[row][c_off + c]  (bias gradients). */
+int msg_bias_grad(int dtype, const void* dy, long long rows, int C_total, int c_off, int C,
+                  float* db, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm2d(affine=False, eps=1e-5, biased variance) -- enhanced_generator.py:54,59,64,69,
+ * 74,93,100,107,122,129,242,246,250,263.  Bandwidth-bound, vectorised, warp-shuffle reductions.
+ * stats are RAW sums fp32 [N][C][2] = (sum x, sum x^2) over the H*W plane.
+ * ------------------------------------------------------------------------------------------- */
+int msg_instnorm_stats(int dtype, const void* x, int N, long long HW, int C, float* stats,
+                       void* stream);
+/* y = act((x - mean) * rstd * gamma + beta) [+ residual];   gamma/beta optional blended affine:
+ * gamma[c] = sum_s w[s]*gammas[s][c] (north_star extension; pass S=0 for the reference's
+ * affine-free norm).  residual may be NULL.  y may alias x. */
+int msg_instnorm_apply(int dtype, const void* x, const float* stats, int N, long long HW, int C,
+                       int act, const void* residual, int S, const float* gammas,
+                       const float* betas, const float* w, void* y, void* stream);
+/* backward of y = act(IN(x)) [+ residual]:  given dy, x (pre-norm) and stats, writes dx.
+ * (d residual = dy is the caller's business.)  scratch: fp32 [N][C][2], zeroed by the callee. */
+int msg_instnorm_bwd(int dtype, const void* x, const float* stats, const void* dy, int N,
+                     long long HW, int C, int act, float* scratch, void* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LocalAttention core (enhanced_generator.py:22-35) on a [N,H,W,3C] qkv map (the 1x1 qkv conv is
+ * msg_conv2d): per ws x ws window, L2-normalise q and k over C per pixel (eps 1e-12), C x C
+ * logits, softmax over the last dim, times v.  out: [N,H,W,C].  No scale, no residual.
+ * ------------------------------------------------------------------------------------------- */
+int msg_local_attn_fwd(int dtype, const void* qkv, int N, int H, int W, int C, int ws, void* out,
+                       void* stream);
+int msg_local_attn_bwd(int dtype, const void* qkv, const void* dout, int N, int H, int W, int C,
+                       int ws, void* dqkv, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * layout / image helpers
+ * ------------------------------------------------------------------------------------------- */
+/* fp32 NCHW [N,C,H,W] -> NHWC dtype [N,H,W,Cp] (channels >= C zero-filled)  and back. */
+int msg_nchw_to_nhwc(int dtype, const float* x, int N, int C, int H, int W, int Cp, void* y,
+                     void* stream);
+int msg_nhwc_to_nchw(int dtype, const void* x, int N, int C, int H, int W, int Cp, float* y,
+                     void* stream);
+/* Multi-style output blend (advanced_transform.py:206-213, direct_transform.py:155-165,
+ * batch_process_images.py:306-309):  out = gain * (sum_s w[s]*ys[s] + w_x * x), optional clamp,
+ * optional (v+1)/2 -> clamp(0,1) -> *255 -> uint8.  ys: S device pointers (host array) to fp32
+ * tensors of `numel` elements.  out_u8 may be NULL; out_f32 may be NULL. */
+int msg_blend_outputs(const float* const* ys, const float* w, int S, const float* x, float w_x,
+                      float gain, int do_clip, float clip_lo, float clip_hi, long long numel,
+                      float* out_f32, uint8_t* out_u8, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * losses (enhanced_train.py:49-52): mean-reduced MSE / L1, forward value and input gradient.
+ * loss_out: device fp32 scalar, ACCUMULATED into (+= scale * mean(...)); grad_a = scale*d/da.
+ * b may be NULL with b_const used instead (ones_like / zeros_like targets, :72-79,100-101).
+ * ------------------------------------------------------------------------------------------- */
+int msg_mse_loss(const float* a, const float* b, float b_const, long long n, float scale,
+                 float* loss_out, float* grad_a, void* stream);
+int msg_l1_loss(const float* a, const float* b, float b_const, long long n, float scale,
+                float* loss_out, float* grad_a, float* grad_b, void* stream);
+
+/* fused Adam (enhanced_train.py:36-43): one launch over a flat fp32 parameter buffer.
+ * grad_scale multiplies the gradient first (1/world_size after the NCCL sum-allreduce). */
+int msg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* spectral norm (old-style torch.nn.utils.spectral_norm, enhanced_generator.py:269-271):
+ * one power iteration on W[rows][cols] (fp32), updating u[rows], v[cols] in place, then
+ * sigma = u^T W v written to *sigma.  do_power_iter=0 (eval) only computes sigma. */
+int msg_spectral_norm(const float* w, int rows, int cols, float* u, float* v, int do_power_iter,
+                      float eps, float* sigma, void* stream);
+/* gradient through weight = weight_orig / sigma:
+ * dw_orig += (dw - <dw, w_orig>/sigma * u v^T) / sigma  */
+int msg_spectral_norm_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
+                          const float* sigma, int rows, int cols, float* dw_orig, float* scratch,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gram matrix + style loss (north_star addition; not in the reference).
+ * feat: [N,H,W,C] dtype.  gram: fp32 [N][C][C] = F F^T / (C*H*W).
+ * msg_gram_loss_fwd: loss += scale * mean((G - target)^2); keeps G for the backward.
+ * msg_gram_loss_bwd: dfeat = scale * 2/(N*C*C) * 2/(C*H*W) * (G - target) . F   (written, dtype).
+ * ------------------------------------------------------------------------------------------- */
+int msg_gram(int dtype, const void* feat, int N, long long HW, int C, float* gram, void* stream);
+int msg_gram_loss_fwd(int dtype, const void* feat, int N, long long HW, int C, const float* target,
+                      float scale, float* gram, float* loss_out, void* stream);
+int msg_gram_loss_bwd(int dtype, const void* feat, int N, long long HW, int C, const float* gram,
+                      const float* target, float scale, void* wscratch /* dtype [N][C][C] */,
+                      void* dfeat, void* stream);
+/* 2x2 max pool (VGG trunk) fwd/bwd on NHWC. */
+int msg_maxpool2x2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
+int msg_maxpool2x2_bwd(int dtype, const void* x, const void* dy, int N, int H, int W, int C,
+                       void* dx, void* stream);
+/* elementwise backward of an activation applied in a conv epilogue: dx = dy * act'(y). */
+int msg_act_bwd(int dtype, const void* y, const void* dy, long long n, int act, void* dx,
+                void* stream);
+/* tanh backward on the fp32 NCHW image: dz (NHWC dtype, Cp channels) = dy * (1 - y^2). */
+int msg_tanh_bwd_nchw(int dtype, const float* y, const float* dy, int N, int C, int H, int W,
+                      int Cp, void* dz, void* stream);
+/* out = a + b (dtype tensors, n elements); used to sum gradient branches. */
+int msg_add(int dtype, const void* a, const void* b, long long n, void* out, void* stream);
+/* mean over the H*W plane of a [N,HW,C] tensor -> fp32 [N][C]  (AdaptiveAvgPool2d(1),
+ * enhanced_generator.py:257) and its backward (broadcast of dy/HW). */
+int msg_avgpool_fwd(int dtype, const void* x, int N, long long HW, int C, float* y, void* stream);
+int msg_avgpool_bwd(int dtype, const float* dy, int N, long long HW, int C, void* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSG_B200_H_ */

@@ -1,0 +1,122 @@
+"""ctypes binding of libmsg_b200.so (the C-ABI declared in include/msg_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, or the device is not a
+B200 (sm_100), every op raises.  Build with ``python -m multi_style_transfer_gan_b200.build``.
+"""
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmsg_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+CONV_STATS, CONV_OUT_NCHW_F32, CONV_IN_NORM, CONV_ACCUM, CONV_FORCE_SIMT = 1, 2, 4, 8, 256
+PACK_FWD, PACK_DGRAD_S1, PACK_CONVT_PHASES = 0, 1, 2
+
+c_int, c_ll, c_float, c_void_p, c_uint = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                                          ctypes.c_void_p, ctypes.c_uint)
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in (
+        "dtype", "N", "Hi", "Wi", "Ci_total", "ci_off", "Cin", "Ho", "Wo", "Co_total", "co_off",
+        "Cout", "Hg", "Wg", "KH", "KW", "in_stride", "pad_h", "pad_w", "dil", "out_stride",
+        "out_off_h", "out_off_w", "act")] + [("flags", c_uint), ("in_act", c_int)]
+
+
+_P = c_void_p
+# name -> argtypes (everything returns int except msg_last_error)
+SIGNATURES = {
+    "msg_version": [],
+    "msg_check_device": [],
+    "msg_sm_count": [],
+    "msg_conv2d": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
+    "msg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
+    "msg_pack_conv_weight": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "msg_unpack_conv_wgrad": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_bias_grad": [c_int, _P, c_ll, c_int, c_int, c_int, _P, _P],
+    "msg_instnorm_stats": [c_int, _P, c_int, c_ll, c_int, _P, _P],
+    "msg_instnorm_apply": [c_int, _P, _P, c_int, c_ll, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P],
+    "msg_instnorm_bwd": [c_int, _P, _P, _P, c_int, c_ll, c_int, c_int, _P, _P, _P],
+    "msg_local_attn_fwd": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_local_attn_bwd": [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_nchw_to_nhwc": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_nhwc_to_nchw": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_blend_outputs": [ctypes.POINTER(_P), ctypes.POINTER(c_float), c_int, _P, c_float, c_float,
+                          c_int, c_float, c_float, c_ll, _P, _P, _P],
+    "msg_mse_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P],
+    "msg_l1_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P, _P],
+    "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],
+    "msg_spectral_norm": [_P, c_int, c_int, _P, _P, c_int, c_float, _P, _P],
+    "msg_spectral_norm_bwd": [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    "msg_gram": [c_int, _P, c_int, c_ll, c_int, _P, _P],
+    "msg_gram_loss_fwd": [c_int, _P, c_int, c_ll, c_int, _P, c_float, _P, _P, _P],
+    "msg_gram_loss_bwd": [c_int, _P, c_int, c_ll, c_int, _P, _P, c_float, _P, _P, _P],
+    "msg_maxpool2x2_fwd": [c_int, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_maxpool2x2_bwd": [c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_act_bwd": [c_int, _P, _P, c_ll, c_int, _P, _P],
+    "msg_tanh_bwd_nchw": [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_add": [c_int, _P, _P, c_ll, _P, _P],
+    "msg_avgpool_fwd": [c_int, _P, c_int, c_ll, c_int, _P, _P],
+    "msg_avgpool_bwd": [c_int, _P, c_int, c_ll, c_int, _P, _P],
+}
+
+_lib = None
+_lock = threading.Lock()
+_device_ok = set()
+
+
+class MsgError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once; raises MsgError (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MsgError(
+                f"{LIB_PATH} not found: the CUDA extension is not built and there is no fallback path. "
+                "Run `python -m multi_style_transfer_gan_b200.build` (needs nvcc).")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale: loud on purpose
+            fn.argtypes = args
+            fn.restype = c_int
+        lib.msg_last_error.argtypes = []
+        lib.msg_last_error.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().msg_last_error()
+        raise MsgError(f"msg_b200 error {rc}: {msg.decode(errors='replace') if msg else ''}")
+
+
+def require_device(index):
+    """Raises unless the *current* CUDA device is sm_100 (checked once per device)."""
+    if index in _device_ok:
+        return
+    check(load().msg_check_device())
+    _device_ok.add(index)
+
+
+# launch counter: every successful C-ABI call that launches kernels bumps this (bench.py's
+# gpu_launches claim is derived from it).
+launches = 0
+
+
+def call(name, *args):
+    global launches
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        check(rc)
+    launches += 1

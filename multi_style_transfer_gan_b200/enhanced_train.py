@@ -1,0 +1,167 @@
+"""Drop-in for the reference's ``EnhancedCycleGAN`` (enhanced_train.py:13-152): same attributes
+(G_AB, G_BA, D_A, D_B, g_optimizer, d_optimizer, device), same ``train_step(real_A, real_B) ->
+dict`` with the five loss keys, same ``save_models`` checkpoint files.
+
+Differences that are deliberate:
+  * mixed precision is bf16 (no GradScaler needed) instead of fp16 autocast + GradScaler
+    (enhanced_train.py:46,61,88); ``precision="fp32"`` gives the parity mode.
+  * parameters of each optimizer live in ONE flat fp32 buffer (views), gradients likewise: one
+    fused Adam launch and -- when torch.distributed is initialised -- one NCCL all-reduce per
+    optimizer per step (data parallel over NVLink; IN statistics are per-sample so no sync-norm).
+  * the reference leaks generator-phase gradients into D's .grad and discards them at the next
+    zero_grad (:67); here they are simply not computed.
+  * the data loop / dataset (enhanced_train.py:154-208) is out of scope: inputs are tensors.
+"""
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .enhanced_generator import EnhancedDiscriminator, EnhancedGenerator
+from .losses import l1, mse_to_const
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas=(0.5,0.999), eps=1e-8) semantics (enhanced_train.py:36-43) as one
+    kernel launch over a flat parameter / gradient buffer.  Parameters are re-pointed to views of
+    the flat buffer at construction."""
+
+    def __init__(self, params, lr, betas=(0.5, 0.999), eps=1e-8):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.flat_grad[off:off + k].view_as(p)
+            off += k
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()   # keep the views alive: autograd accumulates into them in place
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        self.step_count += 1
+        g = self.param_groups[0]
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
+                      g["betas"][1], g["eps"], self.step_count, grad_scale)
+
+
+class EnhancedCycleGAN:
+    def __init__(self, pretrained_path=None, channels=16, num_transformer_blocks=1, precision="bf16",
+                 device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("EnhancedCycleGAN (msg_b200): a B200 GPU is required; there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        c, nb = channels, num_transformer_blocks           # reference: 16 / 1 (enhanced_train.py:18-21)
+        self.G_AB = EnhancedGenerator(channels=c, num_transformer_blocks=nb).to(self.device)
+        self.G_BA = EnhancedGenerator(channels=c, num_transformer_blocks=nb).to(self.device)
+        self.D_A = EnhancedDiscriminator(channels=c).to(self.device)
+        self.D_B = EnhancedDiscriminator(channels=c).to(self.device)
+        self.G_AB.gradient_checkpointing_enable()          # :24-25
+        self.G_BA.gradient_checkpointing_enable()
+        if pretrained_path and Path(pretrained_path).exists():
+            ckpt = torch.load(pretrained_path, map_location=self.device)
+            self.G_AB.load_state_dict(ckpt["model_state_dict"], strict=False)   # :32-33
+            self.G_BA.load_state_dict(ckpt["model_state_dict"], strict=False)
+        self.set_precision(precision)
+        self.lambda_cycle, self.lambda_identity, self.lambda_structure = 10.0, 2.0, 0.5   # :55-57
+        self._build_optimizers()
+
+    def _build_optimizers(self):
+        gp = [p for m in (self.G_AB, self.G_BA) for k, p in m.named_parameters()]
+        dp = [p for m in (self.D_A, self.D_B) for p in m.parameters()]
+        self.g_optimizer = FusedAdam(gp, lr=5e-5, betas=(0.5, 0.999))
+        self.d_optimizer = FusedAdam(dp, lr=2e-4, betas=(0.5, 0.999))
+        for m in (self.G_AB, self.G_BA):
+            m.invalidate_packed_weights()
+
+    def set_precision(self, precision):
+        self.precision = precision
+        for m in (self.G_AB, self.G_BA, self.D_A, self.D_B):
+            m.set_precision(precision)
+
+    def load_state_dicts(self, G_AB=None, G_BA=None, D_A=None, D_B=None):
+        """Loads weights IN PLACE (the flat optimizer buffers stay the parameter storage)."""
+        for m, sd in ((self.G_AB, G_AB), (self.G_BA, G_BA), (self.D_A, D_A), (self.D_B, D_B)):
+            if sd is not None:
+                m.load_state_dict(sd, strict=True)
+        for m in (self.G_AB, self.G_BA):
+            m.invalidate_packed_weights()
+
+    def _sync_grads(self, opt):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)   # one flat NCCL all-reduce
+            return 1.0 / dist.get_world_size()
+        return 1.0
+
+    def train_step(self, real_A, real_B):
+        """reference: enhanced_train.py:59-131 (order of the 6 G and 10 D forwards preserved, so the
+        spectral-norm power iterations advance exactly as in the reference)."""
+        G_AB, G_BA, D_A, D_B = self.G_AB, self.G_BA, self.D_A, self.D_B
+        real_A = real_A.to(self.device, non_blocking=True)
+        real_B = real_B.to(self.device, non_blocking=True)
+        fake_B = G_AB(real_A)
+        fake_A = G_BA(real_B)
+
+        # ---- discriminators (:66-85)
+        self.d_optimizer.zero_grad()
+        for m in (D_A, D_B):
+            m.requires_grad_(True)
+        real_A_score, _ = D_A(real_A)
+        real_B_score, _ = D_B(real_B)
+        d_real_loss = (mse_to_const(real_A_score, 1.0) + mse_to_const(real_B_score, 1.0)) * 0.5
+        fake_A_score, _ = D_A(fake_A.detach())
+        fake_B_score, _ = D_B(fake_B.detach())
+        d_fake_loss = (mse_to_const(fake_A_score, 0.0) + mse_to_const(fake_B_score, 0.0)) * 0.5
+        d_loss = d_real_loss + d_fake_loss
+        d_loss.backward()
+        self.d_optimizer.step(grad_scale=self._sync_grads(self.d_optimizer))
+
+        # ---- generators (:87-123)
+        self.g_optimizer.zero_grad()
+        for m in (D_A, D_B):
+            m.requires_grad_(False)        # no leaked D grads (see module docstring)
+        idt_A = G_BA(real_A)
+        idt_B = G_AB(real_B)
+        identity_loss = (l1(idt_A, real_A) + l1(idt_B, real_B)) * self.lambda_identity
+        fake_A_score, _ = D_A(fake_A)
+        fake_B_score, _ = D_B(fake_B)
+        g_loss = mse_to_const(fake_A_score, 1.0) + mse_to_const(fake_B_score, 1.0)
+        recon_A = G_BA(fake_B)
+        recon_B = G_AB(fake_A)
+        cycle_loss = (l1(recon_A, real_A) + l1(recon_B, real_B)) * self.lambda_cycle
+        _, real_A_struct = D_A(real_A)
+        _, fake_A_struct = D_A(fake_A)
+        _, real_B_struct = D_B(real_B)
+        _, fake_B_struct = D_B(fake_B)
+        structure_loss = (l1(real_A_struct, fake_A_struct) + l1(real_B_struct, fake_B_struct)) * self.lambda_structure
+        total_g_loss = g_loss + cycle_loss + identity_loss + structure_loss
+        total_g_loss.backward()
+        self.g_optimizer.step(grad_scale=self._sync_grads(self.g_optimizer))
+        for m in (D_A, D_B):
+            m.requires_grad_(True)
+        for m in (G_AB, G_BA):
+            m.invalidate_packed_weights()
+
+        vals = torch.stack([d_loss.detach(), g_loss.detach(), cycle_loss.detach(), identity_loss.detach(),
+                            structure_loss.detach()]).tolist()          # one sync instead of five .item()
+        return dict(zip(("d_loss", "g_loss", "cycle_loss", "identity_loss", "structure_loss"), vals))
+
+    def save_models(self, save_dir, epoch):
+        """reference: enhanced_train.py:133-152 (same file names and dict keys)."""
+        save_path = Path(save_dir)
+        save_path.mkdir(parents=True, exist_ok=True)
+        torch.save({"epoch": epoch, "G_AB_state_dict": self.G_AB.state_dict()}, save_path / f"G_AB_epoch_{epoch}.pth")
+        torch.save({"epoch": epoch, "G_BA_state_dict": self.G_BA.state_dict()}, save_path / f"G_BA_epoch_{epoch}.pth")
+        torch.save({"epoch": epoch, "D_A_state_dict": self.D_A.state_dict(), "D_B_state_dict": self.D_B.state_dict()},
+                   save_path / f"discriminators_epoch_{epoch}.pth")

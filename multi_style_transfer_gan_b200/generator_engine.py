@@ -1,0 +1,196 @@
+"""Forward / backward schedule of the EnhancedGenerator on the msg_b200 kernels.
+
+Follows enhanced_generator.py:86-228 of the reference (module structure :91-147, forward
+:211-228).  The engine works on a flat ``{state_dict key: fp32 tensor}`` view of the parameters and
+NHWC activations; it owns no parameters itself.
+
+Per stage (down1/down2/up1/up2, width C), kernels launched in the forward:
+    main conv (4x4 s2 conv | 4 phases of the 4x4 s2 convT)  + IN statistics in the epilogue
+    IN apply + ReLU
+    qkv 1x1 conv -> LocalAttention core -> proj 1x1 conv
+    4 branch convs writing channel slices of ONE [N,H,W,C] tensor (no cat) + shared IN statistics
+    IN apply + ReLU -> fusion 1x1 conv (+ statistics) -> IN apply + ReLU + residual add
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_TANH, ConvGeom
+
+STAGES = ("down1", "down2", "up1", "up2")
+BRANCHES = ((1, 0, 1), (3, 1, 1), (3, 2, 2), (3, 4, 4))  # (k, pad, dil) of branch1..4, :52-71
+
+
+def _pad_dim(t, dim, to):
+    if t.shape[dim] == to:
+        return t
+    pad = [0, 0] * (t.dim() - dim - 1) + [0, to - t.shape[dim]]
+    return F.pad(t, pad)
+
+
+class GeneratorEngine:
+    def __init__(self, channels):
+        c = self.c = channels
+        if c % 4:
+            raise ValueError("EnhancedGenerator: channels must be a multiple of 4 (MultiScaleBlock splits C/4)")
+        self.cin_pad = 4      # image channels 3 -> 4 (zero weights for the pad channel)
+        self.cout_pad = 4     # output conv 3 -> 4 filters (4th is zero, never stored)
+        self.width = {"down1": 2 * c, "down2": 4 * c, "up1": 2 * c, "up2": c}
+        self.inwidth = {"down1": c, "down2": 2 * c, "up1": 4 * c, "up2": 2 * c}
+        g = self.geom = {}
+        g["initial.0"] = ConvGeom("conv", self.cin_pad, c, 7, 1, 3)
+        for s in STAGES:
+            C, Ci = self.width[s], self.inwidth[s]
+            g[f"{s}.0"] = ConvGeom("convT" if s.startswith("up") else "conv", Ci, C, 4, 2, 1)
+            g[f"{s}.3.qkv"] = ConvGeom("conv", C, 3 * C, 1)
+            g[f"{s}.3.proj"] = ConvGeom("conv", C, C, 1)
+            for i, (k, p, d) in enumerate(BRANCHES, start=1):
+                g[f"{s}.4.branch{i}.0"] = ConvGeom("conv", C, C // 4, k, 1, p, d)
+            g[f"{s}.4.fusion.0"] = ConvGeom("conv", C, C, 1)
+        g["output.0"] = ConvGeom("conv", c, self.cout_pad, 7, 1, 3)
+        self._cache = {}
+
+    # ---- packed-weight cache ---------------------------------------------------------------------
+    def invalidate(self):
+        self._cache.clear()
+
+    def _master(self, params, name):
+        w = params[f"{name}.weight"]
+        if name == "initial.0":
+            w = _pad_dim(w, 1, self.cin_pad)
+        elif name == "output.0":
+            w = _pad_dim(w, 0, self.cout_pad)
+        return w.contiguous()
+
+    def _packed(self, params, name, which, dtype):
+        w = params[f"{name}.weight"]
+        key = (name, which, dtype)
+        ver = (w.data_ptr(), w._version)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        m = self._master(params, name)
+        g = self.geom[name]
+        t = g.pack_fwd(m, dtype) if which == "fwd" else g.pack_dgrad(m, dtype)
+        self._cache[key] = (ver, t)
+        return t
+
+    def _bias(self, params, name):
+        b = params[f"{name}.bias"]
+        if name == "output.0":
+            b = _pad_dim(b, 0, self.cout_pad)
+        return b.contiguous()
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def _stage_fwd(self, P, s, a_in, dtype):
+        g = self.geom
+        C = self.width[s]
+        N = a_in.shape[0]
+        dev = a_in.device
+        st0 = ops.new_stats(N, C, dev)
+        y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
+        a0 = ops.instnorm_apply(y0, st0, ACT_RELU)
+        qkv = g[f"{s}.3.qkv"].forward(a0, self._packed(P, f"{s}.3.qkv", "fwd", dtype), self._bias(P, f"{s}.3.qkv"))
+        att = ops.local_attn_fwd(qkv)
+        a1 = g[f"{s}.3.proj"].forward(att, self._packed(P, f"{s}.3.proj", "fwd", dtype), self._bias(P, f"{s}.3.proj"))
+        b = torch.empty_like(a1)
+        stb = ops.new_stats(N, C, dev)
+        for i in range(1, 5):
+            n = f"{s}.4.branch{i}.0"
+            g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
+        bn = ops.instnorm_apply(b, stb, ACT_RELU)
+        stf = ops.new_stats(N, C, dev)
+        n = f"{s}.4.fusion.0"
+        f = g[n].forward(bn, self._packed(P, n, "fwd", dtype), self._bias(P, n), stats=stf)
+        a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1)
+        saved = dict(a_in=a_in, y0=y0, st0=st0, a0=a0, qkv=qkv, att=att, a1=a1, b=b, stb=stb, bn=bn, f=f, stf=stf)
+        return a2, saved
+
+    def encode(self, P, x, dtype, save):
+        """x: fp32 NCHW image -> (a [N,H/4,W/4,4c] NHWC, saved)."""
+        N, Cx, H, W = x.shape
+        if Cx != 3:
+            raise RuntimeError(f"EnhancedGenerator expects 3 input channels, got {Cx}")
+        if H % 16 or W % 16:
+            # the reference's LocalAttention pad path is broken (enhanced_generator.py:15-23): such
+            # sizes raise there too.
+            raise RuntimeError(f"EnhancedGenerator: H and W must be multiples of 16, got {H}x{W}")
+        x0 = ops.nchw_to_nhwc(x, dtype, self.cin_pad)
+        sti = ops.new_stats(N, self.c, x.device)
+        yi = self.geom["initial.0"].forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
+        a = ops.instnorm_apply(yi, sti, ACT_RELU)
+        saved = {"x0": x0, "yi": yi, "sti": sti, "ai": a} if save else None
+        for s in ("down1", "down2"):
+            a, sv = self._stage_fwd(P, s, a, dtype)
+            if save:
+                saved[s] = sv if save == "full" else {"a_in": sv["a_in"]}
+        return a, saved
+
+    def decode(self, P, a, dtype, save):
+        """a: [N,H/4,W/4,4c] NHWC -> (y fp32 NCHW in [-1,1], saved)."""
+        saved = {} if save else None
+        for s in ("up1", "up2"):
+            a, sv = self._stage_fwd(P, s, a, dtype)
+            if save:
+                saved[s] = sv if save == "full" else {"a_in": sv["a_in"]}
+        N, H, W, _ = a.shape
+        y = torch.empty((N, 3, H, W), device=a.device, dtype=torch.float32)
+        go = ConvGeom("conv", self.c, 3, 7, 1, 3)   # store 3 filters of the 4-row packed weight
+        go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0"), act=ACT_TANH, nchw_out=y)
+        if save:
+            saved["a_last"] = a
+            saved["y"] = y
+        return y, saved
+
+    # ---- backward --------------------------------------------------------------------------------
+    def _conv_bwd(self, P, G, name, x, dy, dtype, need_dx=True, in_hw=None, dy_c_off=0, dx_out=None, accumulate=False):
+        """Accumulates weight / bias grads of conv `name` into G and returns dx (or None)."""
+        g = self.geom[name]
+        m = self._master(P, name)
+        dw = torch.zeros_like(m)
+        db = torch.zeros(m.shape[1] if g.kind == "convT" else m.shape[0], device=m.device, dtype=torch.float32)
+        g.wgrad(x, dy, dw, db, dy_c_off=dy_c_off)
+        if name == "initial.0":
+            dw = dw[:, :3].contiguous()
+        if name == "output.0":
+            dw, db = dw[:3].contiguous(), db[:3].contiguous()
+        G[f"{name}.weight"] = dw if f"{name}.weight" not in G else G[f"{name}.weight"] + dw
+        G[f"{name}.bias"] = db if f"{name}.bias" not in G else G[f"{name}.bias"] + db
+        if not need_dx:
+            return None
+        return g.dgrad(dy, self._packed(P, name, "dgrad", dtype), in_hw or x.shape[1:3], out=dx_out,
+                       accumulate=accumulate, dy_c_off=dy_c_off)
+
+    def _stage_bwd(self, P, G, s, sv, da2, dtype):
+        if "y0" not in sv:  # checkpointed: recompute the stage from its input (enhanced_generator.py:186-208)
+            _, sv = self._stage_fwd(P, s, sv["a_in"], dtype)
+        C = self.width[s]
+        df = ops.instnorm_bwd(sv["f"], sv["stf"], da2, ACT_RELU)
+        dbn = self._conv_bwd(P, G, f"{s}.4.fusion.0", sv["bn"], df, dtype)
+        db = ops.instnorm_bwd(sv["b"], sv["stb"], dbn, ACT_RELU)
+        da1 = da2.clone()  # residual path: d(a1) starts as d(a2)
+        for i in range(1, 5):
+            self._conv_bwd(P, G, f"{s}.4.branch{i}.0", sv["a1"], db, dtype, dy_c_off=(i - 1) * (C // 4),
+                           dx_out=da1, accumulate=True)
+        datt = self._conv_bwd(P, G, f"{s}.3.proj", sv["att"], da1, dtype)
+        dqkv = ops.local_attn_bwd(sv["qkv"], datt)
+        da0 = self._conv_bwd(P, G, f"{s}.3.qkv", sv["a0"], dqkv, dtype)
+        dy0 = ops.instnorm_bwd(sv["y0"], sv["st0"], da0, ACT_RELU)
+        return self._conv_bwd(P, G, f"{s}.0", sv["a_in"], dy0, dtype)
+
+    def decode_bwd(self, P, G, saved, dy, dtype):
+        """dy: fp32 NCHW grad of the image.  Returns d(a) at the decoder input (NHWC)."""
+        dz = ops.tanh_bwd_nchw(saved["y"], dy, dtype, self.cout_pad)
+        da = self._conv_bwd(P, G, "output.0", saved["a_last"], dz, dtype)
+        for s in ("up2", "up1"):
+            da = self._stage_bwd(P, G, s, saved[s], da, dtype)
+        return da
+
+    def encode_bwd(self, P, G, saved, da, dtype, need_dx):
+        for s in ("down2", "down1"):
+            da = self._stage_bwd(P, G, s, saved[s], da, dtype)
+        dyi = ops.instnorm_bwd(saved["yi"], saved["sti"], da, ACT_RELU)
+        dx0 = self._conv_bwd(P, G, "initial.0", saved["x0"], dyi, dtype, need_dx=need_dx)
+        if not need_dx:
+            return None
+        return ops.nhwc_to_nchw(dx0, 3)
