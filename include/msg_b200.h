@@ -86,11 +86,11 @@ typedef struct {
   int in_act;                           /* activation applied after the fused input norm        */
 } msg_conv_desc;
 
-/* x, w (packed [Cout][KH*KW*Cin], dtype), bias fp32 [Cout] or NULL, y, stats fp32 [N][Co_total][2]
+/* x, w (packed [Cout][KH*KW*Cin], dtype), bias fp32 [Cout] or NULL, y, stats fp64 [N][Co_total][2]
  * (only with MSG_CONV_STATS; must be zeroed by the caller; accumulates across calls),
- * in_stats fp32 [N][Ci_total][2] raw sums of the input plane (only with MSG_CONV_IN_NORM). */
+ * in_stats fp64 [N][Ci_total][2] raw sums of the input plane (only with MSG_CONV_IN_NORM). */
 int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-               float* stats, const float* in_stats, void* stream);
+               double* stats, const double* in_stats, void* stream);
 
 /* wgrad of the same descriptor: dw[co][th][tw][ci] (fp32, packed layout, ACCUMULATED into) =
  * sum over pixels of dy[..., co] * gathered x[..., ci].  Replaces autograd's conv weight grads for
@@ -116,20 +116,21 @@ int msg_bias_grad(int dtype, const void* dy, long long rows, int C_total, int c_
 /* ---------------------------------------------------------------------------------------------
  * InstanceNorm2d(affine=False, eps=1e-5, biased variance) -- enhanced_generator.py:54,59,64,69,
  * 74,93,100,107,122,129,242,246,250,263.  Bandwidth-bound, vectorised, warp-shuffle reductions.
- * stats are RAW sums fp32 [N][C][2] = (sum x, sum x^2) over the H*W plane.
+ * stats are RAW plane sums, fp64 [N][C][2] = (sum x, sum x^2) over H*W: fp64 makes
+ * var = E[x^2] - mean^2 cancellation-free and the atomics order-independent (parity mode needs it).
  * ------------------------------------------------------------------------------------------- */
-int msg_instnorm_stats(int dtype, const void* x, int N, long long HW, int C, float* stats,
+int msg_instnorm_stats(int dtype, const void* x, int N, long long HW, int C, double* stats,
                        void* stream);
 /* y = act((x - mean) * rstd * gamma + beta) [+ residual];   gamma/beta optional blended affine:
  * gamma[c] = sum_s w[s]*gammas[s][c] (north_star extension; pass S=0 for the reference's
  * affine-free norm).  residual may be NULL.  y may alias x. */
-int msg_instnorm_apply(int dtype, const void* x, const float* stats, int N, long long HW, int C,
+int msg_instnorm_apply(int dtype, const void* x, const double* stats, int N, long long HW, int C,
                        int act, const void* residual, int S, const float* gammas,
                        const float* betas, const float* w, void* y, void* stream);
 /* backward of y = act(IN(x)) [+ residual]:  given dy, x (pre-norm) and stats, writes dx.
- * (d residual = dy is the caller's business.)  scratch: fp32 [N][C][2], zeroed by the callee. */
-int msg_instnorm_bwd(int dtype, const void* x, const float* stats, const void* dy, int N,
-                     long long HW, int C, int act, float* scratch, void* dx, void* stream);
+ * (d residual = dy is the caller's business.)  scratch: fp64 [N][C][2], zeroed by the callee. */
+int msg_instnorm_bwd(int dtype, const void* x, const double* stats, const void* dy, int N,
+                     long long HW, int C, int act, double* scratch, void* dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LocalAttention core (enhanced_generator.py:22-35) on a [N,H,W,3C] qkv map (the 1x1 qkv conv is

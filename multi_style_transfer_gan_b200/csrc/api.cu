@@ -44,13 +44,13 @@ int sm_count() { return dev_info().sms; }
 
 int conv_validate(const msg_conv_desc* d);
 int conv2d_simt(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                float* stats, const float* in_stats, cudaStream_t st);
+                double* stats, const double* in_stats, cudaStream_t st);
 bool conv2d_tc_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
 int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-              float* stats, const float* in_stats, cudaStream_t st);
+              double* stats, const double* in_stats, cudaStream_t st);
 
 int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                    float* stats, const float* in_stats, cudaStream_t st) {
+                    double* stats, const double* in_stats, cudaStream_t st) {
   int rc = conv_validate(d);
   if (rc) return rc;
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_STATS without a stats buffer");
@@ -78,6 +78,6 @@ extern "C" int msg_check_device(void) {
 }
 
 extern "C" int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias,
-                          void* y, float* stats, const float* in_stats, void* stream) {
+                          void* y, double* stats, const double* in_stats, void* stream) {
   return conv2d_dispatch(d, x, w, bias, y, stats, in_stats, as_stream(stream));
 }

@@ -98,12 +98,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr float kInEps = 1e-5f;
 
-// raw sums -> (mean, rstd)
-__device__ __forceinline__ void finalize_stats(float s, float ss, float inv_hw, float& mean, float& rstd) {
-  mean = s * inv_hw;
-  float var = fmaf(-mean, mean, ss * inv_hw);
-  var = var > 0.f ? var : 0.f;
-  rstd = rsqrtf(var + kInEps);
+// raw plane sums (kept in fp64: E[x^2]-mean^2 then has no cancellation problem and the fp64 atomics
+// make the statistics order-independent to ~1e-16) -> (mean, rstd) in fp32
+__device__ __forceinline__ void finalize_stats(double s, double ss, double inv_hw, float& mean, float& rstd) {
+  double m = s * inv_hw;
+  double var = ss * inv_hw - m * m;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)kInEps));
 }
 
 int sm_count();

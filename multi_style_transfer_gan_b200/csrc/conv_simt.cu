@@ -41,7 +41,7 @@ __device__ __forceinline__ size_t out_pixel_offset(const msg_conv_desc& d, long 
 // Gather 4 consecutive K elements (k0..k0+3) of the im2col row `rc` into v[].
 template <typename T, bool VEC>
 __device__ __forceinline__ void gather4(const msg_conv_desc& d, const T* __restrict__ x,
-                                        const float* __restrict__ in_stats, float inv_hw_in,
+                                        const double* __restrict__ in_stats, double inv_hw_in,
                                         const RowCoord& rc, int k0, int K, float (&v)[4]) {
   v[0] = v[1] = v[2] = v[3] = 0.f;
   if (!rc.valid || k0 >= K) return;
@@ -53,7 +53,7 @@ __device__ __forceinline__ void gather4(const msg_conv_desc& d, const T* __restr
     size_t off = (((size_t)rc.n * d.Hi + ih) * d.Wi + iw) * d.Ci_total + d.ci_off + ci;
     load4(x + off, v);
     if (d.flags & MSG_CONV_IN_NORM) {
-      const float* st = in_stats + ((size_t)rc.n * d.Ci_total + d.ci_off + ci) * 2;
+      const double* st = in_stats + ((size_t)rc.n * d.Ci_total + d.ci_off + ci) * 2;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float mean, rstd;
@@ -73,7 +73,7 @@ __device__ __forceinline__ void gather4(const msg_conv_desc& d, const T* __restr
       size_t off = (((size_t)rc.n * d.Hi + ih) * d.Wi + iw) * d.Ci_total + d.ci_off + ci;
       float val = to_f<T>(x[off]);
       if (d.flags & MSG_CONV_IN_NORM) {
-        const float* st = in_stats + ((size_t)rc.n * d.Ci_total + d.ci_off + ci) * 2;
+        const double* st = in_stats + ((size_t)rc.n * d.Ci_total + d.ci_off + ci) * 2;
         float mean, rstd;
         finalize_stats(st[0], st[1], inv_hw_in, mean, rstd);
         val = apply_act((val - mean) * rstd, d.in_act);
@@ -86,8 +86,8 @@ __device__ __forceinline__ void gather4(const msg_conv_desc& d, const T* __restr
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __restrict__ w,
-                 const float* __restrict__ bias, void* __restrict__ yv, float* __restrict__ stats,
-                 const float* __restrict__ in_stats) {
+                 const float* __restrict__ bias, void* __restrict__ yv, double* __restrict__ stats,
+                 const double* __restrict__ in_stats) {
   __shared__ __align__(16) float As[BK][LDS];
   __shared__ __align__(16) float Bs[BK][LDS];
   const int tid = threadIdx.x;
@@ -95,7 +95,7 @@ conv_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __rest
   const long long M = (long long)d.N * d.Hg * d.Wg;
   const long long m0 = (long long)blockIdx.x * BM;
   const int co0 = blockIdx.y * BN;
-  const float inv_hw_in = 1.f / ((float)d.Hi * (float)d.Wi);
+  const double inv_hw_in = 1.0 / ((double)d.Hi * (double)d.Wi);
 
   const int lrow = tid >> 2, kc = (tid & 3) * 4;
   const RowCoord rc = decode_row(d, m0 + lrow, M);
@@ -175,9 +175,9 @@ conv_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __rest
         float ts = 0.f, tss = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) { ts += As[r][tid]; tss += Bs[r][tid]; }
-        float* st = stats + ((size_t)n_first * d.Co_total + d.co_off + co0 + tid) * 2;
-        atomicAdd(st, ts);
-        atomicAdd(st + 1, tss);
+        double* st = stats + ((size_t)n_first * d.Co_total + d.co_off + co0 + tid) * 2;
+        atomicAdd(st, (double)ts);
+        atomicAdd(st + 1, (double)tss);
       }
     } else {
 #pragma unroll
@@ -189,9 +189,9 @@ conv_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __rest
         for (int j = 0; j < 4; ++j) {
           int co = co0 + tx * 4 + j;
           if (co >= d.Cout) continue;
-          float* st = stats + ((size_t)n * d.Co_total + d.co_off + co) * 2;
-          atomicAdd(st, acc[i][j]);
-          atomicAdd(st + 1, acc[i][j] * acc[i][j]);
+          double* st = stats + ((size_t)n * d.Co_total + d.co_off + co) * 2;
+          atomicAdd(st, (double)acc[i][j]);
+          atomicAdd(st + 1, (double)acc[i][j] * (double)acc[i][j]);
         }
       }
     }
@@ -242,7 +242,7 @@ constexpr int WP = 16;  // pixels per reduction chunk
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 conv_wgrad_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __restrict__ dy,
-                       float* __restrict__ dw, const float* __restrict__ in_stats,
+                       float* __restrict__ dw, const double* __restrict__ in_stats,
                        long long pixels_per_split) {
   __shared__ __align__(16) float Ds[WP][LDS];  // dy tile  [pixel][co]
   __shared__ __align__(16) float As[WP][LDS];  // im2col   [pixel][k]
@@ -252,7 +252,7 @@ conv_wgrad_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* 
   const int k0b = blockIdx.x * 64, co0 = blockIdx.y * 64;
   long long m_begin = (long long)blockIdx.z * pixels_per_split;
   long long m_end = m_begin + pixels_per_split < M ? m_begin + pixels_per_split : M;
-  const float inv_hw_in = 1.f / ((float)d.Hi * (float)d.Wi);
+  const double inv_hw_in = 1.0 / ((double)d.Hi * (double)d.Wi);
   const int p = tid >> 4, c4 = (tid & 15) * 4;
   const int ty = tid >> 4, tx = tid & 15;
   const bool dy_vec = VEC && ((d.Co_total | d.co_off) & 3) == 0;
@@ -411,7 +411,7 @@ int validate_desc(const msg_conv_desc* d) {
 }  // namespace
 
 int conv2d_simt(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                float* stats, const float* in_stats, cudaStream_t st) {
+                double* stats, const double* in_stats, cudaStream_t st) {
   const long long M = (long long)d->N * d->Hg * d->Wg;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->Cout + BN - 1) / BN));
   const bool vec = (d->Cin % 4 == 0) && (d->Ci_total % 4 == 0) && (d->ci_off % 4 == 0);
@@ -453,7 +453,7 @@ extern "C" int msg_conv2d_wgrad(const msg_conv_desc* d, const void* x, const voi
   dim3 grid(gx, gy, gz);
   cudaStream_t st = as_stream(stream);
   const bool vec = (d->Cin % 4 == 0) && (d->Ci_total % 4 == 0) && (d->ci_off % 4 == 0);
-  const float* in_stats = nullptr;
+  const double* in_stats = nullptr;
   MSG_REQUIRE(!(d->flags & MSG_CONV_IN_NORM), MSG_ERR_UNSUPPORTED, "wgrad: fused input norm unsupported");
   if (d->dtype == MSG_F32) {
     if (vec) conv_wgrad_simt_kernel<float, true><<<grid, 256, 0, st>>>(*d, (const float*)x, (const float*)dy, dw_packed, in_stats, per);

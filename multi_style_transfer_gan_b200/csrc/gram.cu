@@ -10,7 +10,7 @@
 
 namespace msg {
 int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                    float* stats, const float* in_stats, cudaStream_t st);
+                    double* stats, const double* in_stats, cudaStream_t st);
 namespace {
 
 constexpr int GP = 16;

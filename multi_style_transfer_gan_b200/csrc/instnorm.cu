@@ -33,7 +33,7 @@ constexpr int TPB = 256;
 // x: [N][HW][C]; requires C % W == 0 and (TPB*W) % C == 0 (C a power of two <= TPB*W).
 template <typename T>
 __global__ void __launch_bounds__(TPB)
-in_stats_kernel(const T* __restrict__ x, long long HW, int C, float* __restrict__ stats) {
+in_stats_kernel(const T* __restrict__ x, long long HW, int C, double* __restrict__ stats) {
   constexpr int W = Vec<T>::W;
   __shared__ float red[TPB][2 * W + 1];
   const int n = blockIdx.y;
@@ -57,16 +57,16 @@ in_stats_kernel(const T* __restrict__ x, long long HW, int C, float* __restrict_
     int g = c / W, e = c - g * W;
     float ts = 0.f, tss = 0.f;
     for (int t = g; t < TPB; t += groups) { ts += red[t][e]; tss += red[t][W + e]; }
-    float* st = stats + ((size_t)n * C + c) * 2;
-    atomicAdd(st, ts);
-    atomicAdd(st + 1, tss);
+    double* st = stats + ((size_t)n * C + c) * 2;
+    atomicAdd(st, (double)ts);
+    atomicAdd(st + 1, (double)tss);
   }
 }
 
 // generic fallback: one block per (n, c) plane
 template <typename T>
 __global__ void __launch_bounds__(TPB)
-in_stats_generic_kernel(const T* __restrict__ x, long long HW, int C, float* __restrict__ stats) {
+in_stats_generic_kernel(const T* __restrict__ x, long long HW, int C, double* __restrict__ stats) {
   __shared__ float rs[TPB / 32], rss[TPB / 32];
   const int n = blockIdx.y, c = blockIdx.x;
   const T* xp = x + (size_t)n * HW * C + c;
@@ -81,20 +81,20 @@ in_stats_generic_kernel(const T* __restrict__ x, long long HW, int C, float* __r
   if (threadIdx.x == 0) {
     float a = 0.f, b = 0.f;
     for (int i = 0; i < TPB / 32; ++i) { a += rs[i]; b += rss[i]; }
-    float* st = stats + ((size_t)n * C + c) * 2;
-    st[0] += a; st[1] += b;
+    double* st = stats + ((size_t)n * C + c) * 2;
+    st[0] += (double)a; st[1] += (double)b;
   }
 }
 
 // ---- apply ----------------------------------------------------------------------------------
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(TPB)
-in_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, long long HW, int C,
+in_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, long long HW, int C,
                 int act, const T* __restrict__ residual, int S, const float* __restrict__ gammas,
                 const float* __restrict__ betas, const float* __restrict__ w, T* __restrict__ y) {
   constexpr int W = FAST ? Vec<T>::W : 1;
   const int n = blockIdx.y;
-  const float inv_hw = 1.f / (float)HW;
+  const double inv_hw = 1.0 / (double)HW;
   const size_t base = (size_t)n * HW * C;
   const long long nvec = HW * C / W;
   const long long stride = (long long)gridDim.x * TPB;
@@ -107,7 +107,7 @@ in_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, long l
       c_cached = c0;
 #pragma unroll
       for (int e = 0; e < W; ++e) {
-        const float* st = stats + ((size_t)n * C + c0 + e) * 2;
+        const double* st = stats + ((size_t)n * C + c0 + e) * 2;
         float mean, rstd;
         finalize_stats(st[0], st[1], inv_hw, mean, rstd);
         float g = 1.f, b = 0.f;
@@ -145,13 +145,13 @@ in_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, long l
 // pass 1: scratch[n][c] += (sum g, sum g*xhat) with g = dy * act'(xhat)
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(TPB)
-in_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+in_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats,
                      const T* __restrict__ dy, long long HW, int C, int act,
-                     float* __restrict__ scratch) {
+                     double* __restrict__ scratch) {
   constexpr int W = FAST ? Vec<T>::W : 1;
   __shared__ float red[TPB][2 * W + 1];
   const int n = blockIdx.y;
-  const float inv_hw = 1.f / (float)HW;
+  const double inv_hw = 1.0 / (double)HW;
   const size_t base = (size_t)n * HW * C;
   if constexpr (FAST) {
     const long long nvec = HW * C / W;
@@ -161,7 +161,7 @@ in_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ stats,
     int c0 = (int)((v0 * W) % C);
 #pragma unroll
     for (int e = 0; e < W; ++e) {
-      const float* st = stats + ((size_t)n * C + c0 + e) * 2;
+      const double* st = stats + ((size_t)n * C + c0 + e) * 2;
       finalize_stats(st[0], st[1], inv_hw, mean[e], rstd[e]);
       sg[e] = 0.f; sgx[e] = 0.f;
     }
@@ -184,14 +184,14 @@ in_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ stats,
       int gi = c / W, e = c - gi * W;
       float a = 0.f, b = 0.f;
       for (int t = gi; t < TPB; t += groups) { a += red[t][e]; b += red[t][W + e]; }
-      float* sc = scratch + ((size_t)n * C + c) * 2;
-      atomicAdd(sc, a);
-      atomicAdd(sc + 1, b);
+      double* sc = scratch + ((size_t)n * C + c) * 2;
+      atomicAdd(sc, (double)a);
+      atomicAdd(sc + 1, (double)b);
     }
   } else {
     // generic: grid.x == C, one block per plane
     const int c = blockIdx.x;
-    const float* st = stats + ((size_t)n * C + c) * 2;
+    const double* st = stats + ((size_t)n * C + c) * 2;
     float mean, rstd;
     finalize_stats(st[0], st[1], inv_hw, mean, rstd);
     float sg = 0.f, sgx = 0.f;
@@ -206,8 +206,8 @@ in_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ stats,
     if (threadIdx.x == 0) {
       float a = 0.f, b = 0.f;
       for (int i = 0; i < TPB / 32; ++i) { a += red[i][0]; b += red[i][1]; }
-      float* sc = scratch + ((size_t)n * C + c) * 2;
-      sc[0] += a; sc[1] += b;
+      double* sc = scratch + ((size_t)n * C + c) * 2;
+      sc[0] += (double)a; sc[1] += (double)b;
     }
   }
 }
@@ -215,12 +215,12 @@ in_bwd_reduce_kernel(const T* __restrict__ x, const float* __restrict__ stats,
 // pass 2: dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(TPB)
-in_bwd_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+in_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats,
                     const T* __restrict__ dy, long long HW, int C, int act,
-                    const float* __restrict__ scratch, T* __restrict__ dx) {
+                    const double* __restrict__ scratch, T* __restrict__ dx) {
   constexpr int W = FAST ? Vec<T>::W : 1;
   const int n = blockIdx.y;
-  const float inv_hw = 1.f / (float)HW;
+  const double inv_hw = 1.0 / (double)HW;
   const size_t base = (size_t)n * HW * C;
   const long long nvec = HW * C / W;
   const long long stride = (long long)gridDim.x * TPB;
@@ -233,10 +233,10 @@ in_bwd_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats,
       c_cached = c0;
 #pragma unroll
       for (int e = 0; e < W; ++e) {
-        const float* st = stats + ((size_t)n * C + c0 + e) * 2;
+        const double* st = stats + ((size_t)n * C + c0 + e) * 2;
         finalize_stats(st[0], st[1], inv_hw, mean[e], rstd[e]);
-        const float* sc = scratch + ((size_t)n * C + c0 + e) * 2;
-        mg[e] = sc[0] * inv_hw; mgx[e] = sc[1] * inv_hw;
+        const double* sc = scratch + ((size_t)n * C + c0 + e) * 2;
+        mg[e] = (float)(sc[0] * inv_hw); mgx[e] = (float)(sc[1] * inv_hw);
       }
     }
     float t[W], g[W];
@@ -272,7 +272,7 @@ unsigned blocks_per_image(int N, long long nvec) {
 }
 
 template <typename T>
-int stats_impl(const T* x, int N, long long HW, int C, float* stats, cudaStream_t st) {
+int stats_impl(const T* x, int N, long long HW, int C, double* stats, cudaStream_t st) {
   if (fast_ok<T>(C, HW)) {
     dim3 grid(blocks_per_image(N, HW * C / Vec<T>::W), N);
     in_stats_kernel<T><<<grid, TPB, 0, st>>>(x, HW, C, stats);
@@ -284,7 +284,7 @@ int stats_impl(const T* x, int N, long long HW, int C, float* stats, cudaStream_
 }
 
 template <typename T>
-int apply_impl(const T* x, const float* stats, int N, long long HW, int C, int act, const T* res,
+int apply_impl(const T* x, const double* stats, int N, long long HW, int C, int act, const T* res,
                int S, const float* gammas, const float* betas, const float* w, T* y, cudaStream_t st) {
   if (fast_ok<T>(C, HW)) {
     dim3 grid(blocks_per_image(N, HW * C / Vec<T>::W), N);
@@ -297,9 +297,9 @@ int apply_impl(const T* x, const float* stats, int N, long long HW, int C, int a
 }
 
 template <typename T>
-int bwd_impl(const T* x, const float* stats, const T* dy, int N, long long HW, int C, int act,
-             float* scratch, T* dx, cudaStream_t st) {
-  cudaMemsetAsync(scratch, 0, (size_t)N * C * 2 * sizeof(float), st);
+int bwd_impl(const T* x, const double* stats, const T* dy, int N, long long HW, int C, int act,
+             double* scratch, T* dx, cudaStream_t st) {
+  cudaMemsetAsync(scratch, 0, (size_t)N * C * 2 * sizeof(double), st);
   if (fast_ok<T>(C, HW)) {
     dim3 grid(blocks_per_image(N, HW * C / Vec<T>::W), N);
     in_bwd_reduce_kernel<T, true><<<grid, TPB, 0, st>>>(x, stats, dy, HW, C, act, scratch);
@@ -319,14 +319,14 @@ int bwd_impl(const T* x, const float* stats, const T* dy, int N, long long HW, i
 using namespace msg;
 
 extern "C" int msg_instnorm_stats(int dtype, const void* x, int N, long long HW, int C,
-                                  float* stats, void* stream) {
+                                  double* stats, void* stream) {
   MSG_REQUIRE(N > 0 && HW > 0 && C > 0, MSG_ERR_SHAPE, "instnorm_stats: bad shape");
   if (dtype == MSG_F32) return stats_impl<float>((const float*)x, N, HW, C, stats, as_stream(stream));
   if (dtype == MSG_BF16) return stats_impl<__nv_bfloat16>((const __nv_bfloat16*)x, N, HW, C, stats, as_stream(stream));
   MSG_REQUIRE(false, MSG_ERR_UNSUPPORTED, "instnorm_stats: bad dtype");
 }
 
-extern "C" int msg_instnorm_apply(int dtype, const void* x, const float* stats, int N, long long HW,
+extern "C" int msg_instnorm_apply(int dtype, const void* x, const double* stats, int N, long long HW,
                                   int C, int act, const void* residual, int S, const float* gammas,
                                   const float* betas, const float* w, void* y, void* stream) {
   MSG_REQUIRE(N > 0 && HW > 0 && C > 0, MSG_ERR_SHAPE, "instnorm_apply: bad shape");
@@ -339,8 +339,8 @@ extern "C" int msg_instnorm_apply(int dtype, const void* x, const float* stats, 
   MSG_REQUIRE(false, MSG_ERR_UNSUPPORTED, "instnorm_apply: bad dtype");
 }
 
-extern "C" int msg_instnorm_bwd(int dtype, const void* x, const float* stats, const void* dy, int N,
-                                long long HW, int C, int act, float* scratch, void* dx, void* stream) {
+extern "C" int msg_instnorm_bwd(int dtype, const void* x, const double* stats, const void* dy, int N,
+                                long long HW, int C, int act, double* scratch, void* dx, void* stream) {
   MSG_REQUIRE(N > 0 && HW > 0 && C > 0, MSG_ERR_SHAPE, "instnorm_bwd: bad shape");
   MSG_REQUIRE(act == MSG_ACT_NONE || act == MSG_ACT_RELU || act == MSG_ACT_LRELU, MSG_ERR_UNSUPPORTED, "instnorm_bwd: bad act");
   if (dtype == MSG_F32)

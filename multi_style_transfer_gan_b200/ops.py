@@ -198,7 +198,7 @@ def bias_grad(dy, db, c_off=0, C=None):
 
 # ---- InstanceNorm -------------------------------------------------------------------------------
 def new_stats(N, C, device):
-    return torch.zeros((N, C, 2), device=device, dtype=torch.float32)
+    return torch.zeros((N, C, 2), device=device, dtype=torch.float64)
 
 
 def instnorm_stats(x, stats=None):
@@ -226,7 +226,7 @@ def instnorm_bwd(x, stats, dy, act=ACT_RELU, out=None):
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
-    scratch = torch.empty((N, C, 2), device=x.device, dtype=torch.float32)
+    scratch = torch.empty((N, C, 2), device=x.device, dtype=torch.float64)
     _lib.call("msg_instnorm_bwd", _dt(x), _p(x), _p(stats), _p(dy), N, H * W, C, act, _p(scratch), _p(out), _stream())
     return out
 

@@ -1,0 +1,295 @@
+"""GPU parity tests, op by op, through the C-ABI: each kernel against a plain PyTorch fp32
+restatement of the same op (run on the GPU for speed; TF32 disabled)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+TOL = {torch.float32: 2e-5, torch.bfloat16: 2e-2}
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def q(x, dtype):
+    """round-trip through dtype so the fp32 reference sees the same operand values"""
+    return x.to(dtype).float()
+
+
+CONV_CASES = [
+    # kind, Cin, Cout, k, s, p, d, H, W
+    ("conv", 16, 32, 1, 1, 0, 1, 12, 20),
+    ("conv", 32, 8, 3, 1, 1, 1, 12, 20),
+    ("conv", 32, 8, 3, 1, 2, 2, 12, 20),
+    ("conv", 32, 8, 3, 1, 4, 4, 12, 20),
+    ("conv", 16, 32, 4, 2, 1, 1, 16, 24),
+    ("conv", 4, 16, 7, 1, 3, 1, 16, 16),
+    ("conv", 16, 4, 7, 1, 3, 1, 16, 16),
+    ("conv", 64, 1, 4, 1, 1, 1, 8, 8),
+    ("conv", 6, 10, 3, 1, 1, 1, 9, 7),       # odd channel counts -> scalar path
+    ("convT", 32, 16, 4, 2, 1, 1, 8, 12),
+    ("conv", 64, 128, 4, 2, 1, 1, 32, 32),
+    ("conv", 128, 128, 1, 1, 0, 1, 16, 16),
+    ("convT", 128, 64, 4, 2, 1, 1, 16, 16),
+    ("conv", 256, 64, 3, 1, 2, 2, 16, 16),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_fwd_dgrad_wgrad(case, dtype):
+    from multi_style_transfer_gan_b200 import ops
+    kind, Cin, Cout, k, s, p, d, H, W = case
+    torch.manual_seed(0)
+    g = ops.ConvGeom(kind, Cin, Cout, k, s, p, d)
+    N = 2
+    x = q(torch.randn(N, Cin, H, W, device=DEV), dtype)
+    w = q(torch.randn(*g.weight_shape(), device=DEV) * (1.0 / (Cin * k * k) ** 0.5), dtype)
+    b = torch.randn(Cout, device=DEV)
+    if kind == "convT":
+        ref = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    else:
+        ref = F.conv2d(x, w, b, stride=s, padding=p, dilation=d)
+    wp = g.pack_fwd(w.contiguous(), dtype)
+    stats = ops.new_stats(N, Cout, DEV)
+    y = g.forward(nhwc(x, dtype), wp, b, stats=stats)
+    tol = TOL[dtype]
+    assert_parity(nchw(y), ref, tol, "fwd")
+    # fused statistics epilogue == plane sums of the fp32 result
+    st_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], dim=-1)
+    assert_parity(stats, st_ref, 1e-4 if dtype == torch.float32 else 2e-3, "stats")
+    # dgrad / wgrad / bias grad against autograd
+    dy = q(torch.randn_like(ref), dtype)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    if kind == "convT":
+        out = F.conv_transpose2d(xr, wr, br, stride=2, padding=1)
+    else:
+        out = F.conv2d(xr, wr, br, stride=s, padding=p, dilation=d)
+    out.backward(dy)
+    dx = g.dgrad(nhwc(dy, dtype), g.pack_dgrad(w.contiguous(), dtype), (H, W))
+    assert_parity(nchw(dx), xr.grad, tol, "dgrad")
+    dw = torch.zeros_like(w)
+    db = torch.zeros(Cout, device=DEV)
+    g.wgrad(nhwc(x, dtype), nhwc(dy, dtype), dw, db)
+    assert_parity(dw, wr.grad, 1e-4 if dtype == torch.float32 else 1e-2, "wgrad")
+    assert_parity(db, br.grad, 1e-4 if dtype == torch.float32 else 1e-2, "bias grad")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_channel_slices_and_accumulate(dtype):
+    """branch convs write channel slices of one tensor (no cat); dgrads accumulate (fan-out sum)."""
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(1)
+    N, C, H, W = 2, 32, 8, 12
+    x = q(torch.randn(N, C, H, W, device=DEV), dtype)
+    out = torch.zeros(N, H, W, C, device=DEV, dtype=dtype)
+    refs = []
+    ws = []
+    for i, (k, p, d) in enumerate([(1, 0, 1), (3, 1, 1), (3, 2, 2), (3, 4, 4)]):
+        g = ops.ConvGeom("conv", C, C // 4, k, 1, p, d)
+        w = q(torch.randn(C // 4, C, k, k, device=DEV) * 0.1, dtype)
+        ws.append((g, w))
+        g.forward(nhwc(x, dtype), g.pack_fwd(w, dtype), None, out=out, co_off=i * (C // 4))
+        refs.append(F.conv2d(x, w, None, padding=p, dilation=d))
+    ref = torch.cat(refs, 1)
+    assert_parity(nchw(out), ref, TOL[dtype], "slices")
+    dy = q(torch.randn_like(ref), dtype)
+    xr = x.clone().requires_grad_(True)
+    torch.cat([F.conv2d(xr, w, None, padding=g.pad, dilation=g.dil) for g, w in ws], 1).backward(dy)
+    dx = torch.zeros(N, H, W, C, device=DEV, dtype=dtype)
+    for i, (g, w) in enumerate(ws):
+        g.dgrad(nhwc(dy, dtype), g.pack_dgrad(w, dtype), (H, W), out=dx, accumulate=True, dy_c_off=i * (C // 4))
+    assert_parity(nchw(dx), xr.grad, TOL[dtype] * 2, "accumulated dgrad")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(16, 8, 8), (64, 32, 24), (256, 16, 16), (24, 8, 12), (512, 4, 4)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_instnorm_fwd_bwd(dtype, C, H, W, act):
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(2)
+    N = 3
+    x = q(torch.randn(N, C, H, W, device=DEV) * 2 + 0.5, dtype)
+    res = q(torch.randn(N, C, H, W, device=DEV), dtype)
+    f = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.2)}[act]
+    xr = x.clone().requires_grad_(True)
+    ref = f(F.instance_norm(xr, eps=1e-5)) + res
+    st = ops.instnorm_stats(nhwc(x, dtype))
+    assert_parity(st[..., 0], x.sum((2, 3)), 1e-4, "sum")
+    y = ops.instnorm_apply(nhwc(x, dtype), st, act, residual=nhwc(res, dtype))
+    assert_parity(nchw(y), ref, TOL[dtype], "apply")
+    dy = q(torch.randn_like(ref), dtype)
+    ref.backward(dy)
+    dx = ops.instnorm_bwd(nhwc(x, dtype), st, nhwc(dy, dtype), act)
+    assert_parity(nchw(dx), xr.grad, 1e-4 if dtype == torch.float32 else 3e-2, "bwd")
+
+
+def test_instnorm_blended_affine():
+    """north_star extension; identity affine (gamma=1, beta=0) must reproduce the reference norm."""
+    from multi_style_transfer_gan_b200 import ops
+    from oracle import restate as R
+    torch.manual_seed(3)
+    N, C, H, W, S = 2, 32, 8, 8, 3
+    x = torch.randn(N, C, H, W, device=DEV)
+    gam, bet = torch.randn(S, C, device=DEV), torch.randn(S, C, device=DEV)
+    w = torch.tensor([0.2, 0.3, 0.5], device=DEV)
+    st = ops.instnorm_stats(nhwc(x, torch.float32))
+    y = ops.instnorm_apply(nhwc(x, torch.float32), st, 0, gammas=gam, betas=bet, w=w)
+    assert_parity(nchw(y), R.blended_affine_instance_norm(x.cpu(), gam.cpu(), bet.cpu(), w.cpu()), 2e-5, "blend affine")
+    y1 = ops.instnorm_apply(nhwc(x, torch.float32), st, 0, gammas=torch.ones(S, C, device=DEV),
+                            betas=torch.zeros(S, C, device=DEV), w=w)
+    assert_parity(nchw(y1), R.instance_norm(x.cpu()), 2e-5, "identity affine")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(8, 8, 8), (32, 16, 24), (128, 8, 8), (256, 8, 4)])
+def test_local_attention_core(dtype, C, H, W):
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(4)
+    N = 2
+    qkv = q(torch.randn(N, 3 * C, H, W, device=DEV), dtype).requires_grad_(True)
+
+    def ref_core(t):
+        qq, kk, vv = t.chunk(3, dim=1)
+        def win(u):
+            return u.reshape(N, C, H // 4, 4, W // 4, 4).permute(0, 2, 4, 1, 3, 5).reshape(-1, C, 16)
+        qq, kk, vv = win(qq), win(kk), win(vv)
+        a = torch.softmax(F.normalize(qq, dim=1) @ F.normalize(kk, dim=1).transpose(1, 2), dim=-1)
+        o = a @ vv
+        return o.reshape(N, H // 4, W // 4, C, 4, 4).permute(0, 3, 1, 4, 2, 5).reshape(N, C, H, W)
+
+    ref = ref_core(qkv)
+    out = ops.local_attn_fwd(nhwc(qkv.detach(), dtype))
+    assert_parity(nchw(out), ref, TOL[dtype], "fwd")
+    dy = q(torch.randn_like(ref), dtype)
+    ref.backward(dy)
+    dqkv = ops.local_attn_bwd(nhwc(qkv.detach(), dtype), nhwc(dy, dtype))
+    assert_parity(nchw(dqkv), qkv.grad, 1e-4 if dtype == torch.float32 else 3e-2, "bwd")
+
+
+def test_local_attention_bad_size():
+    from multi_style_transfer_gan_b200 import ops, _lib
+    with pytest.raises(_lib.MsgError):
+        ops.local_attn_fwd(torch.zeros(1, 6, 8, 24, device=DEV))
+
+
+def test_layout_and_blend():
+    from multi_style_transfer_gan_b200 import ops
+    from oracle import restate as R
+    torch.manual_seed(5)
+    x = torch.rand(2, 3, 16, 24, device=DEV) * 2 - 1
+    a = ops.nchw_to_nhwc(x, torch.float32, 4)
+    assert a.shape == (2, 16, 24, 4) and float(a[..., 3].abs().max()) == 0.0
+    assert torch.equal(ops.nhwc_to_nchw(a, 3), x)
+    ys = [torch.rand_like(x) * 2 - 1 for _ in range(3)]
+    w = [0.2, 0.3, 0.5]
+    # advanced_transform.py:206-213: weights [0.2,0.3,0.5], x1.1, clip
+    out = ops.blend_outputs(ys, w, gain=1.1, clip=(-1.0, 1.0))
+    ref = R.blend_outputs([y.cpu() for y in ys], w, gain=1.1, clip=(-1.0, 1.0))
+    assert_parity(out, ref, 1e-6, "blend3")
+    # direct_transform.py:155-165: y*w + x*(1-w)
+    out, u8 = ops.blend_outputs(ys[:1], [0.7], x=x, w_x=0.3, out_uint8=True)
+    ref = R.blend_outputs([ys[0].cpu()], [0.7], x=x.cpu(), w_x=0.3)
+    assert_parity(out, ref, 1e-6, "blend with input")
+    assert (u8.cpu().int() - R.to_uint8_image(ref).int()).abs().max() <= 1
+    assert u8.dtype == torch.uint8
+
+
+def test_losses_adam_spectral():
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(6)
+    a = torch.randn(1000, device=DEV, requires_grad=True)
+    b = torch.randn(1000, device=DEV)
+    l, ga = ops.mse_loss(a.detach(), b, scale=0.5)
+    ref = 0.5 * F.mse_loss(a, b)
+    ref.backward()
+    assert_parity(l.reshape(()), ref, 1e-5, "mse")
+    assert_parity(ga, a.grad, 1e-5, "mse grad")
+    a.grad = None
+    l, ga, gb = ops.l1_loss(a.detach(), b, want_grad_b=True)
+    ref = F.l1_loss(a, b)
+    ref.backward()
+    assert_parity(l.reshape(()), ref, 1e-5, "l1")
+    assert_parity(ga, a.grad, 1e-6, "l1 grad")
+    assert_parity(gb, -a.grad, 1e-6, "l1 grad b")
+    l, _ = ops.mse_loss(a.detach(), None, b_const=1.0, want_grad=False)
+    assert_parity(l.reshape(()), F.mse_loss(a.detach(), torch.ones_like(a)), 1e-5, "mse const")
+    # Adam, 3 steps against torch.optim.Adam
+    p = torch.randn(5000, device=DEV)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=2e-4, betas=(0.5, 0.999))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        pr.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, 2e-4, 0.5, 0.999, 1e-8, step)
+    assert_parity(p, pr.detach(), 1e-6, "adam")
+    # spectral norm power iteration
+    w = torch.randn(24, 40, device=DEV)
+    u = F.normalize(torch.randn(24, device=DEV), dim=0)
+    v = F.normalize(torch.randn(40, device=DEV), dim=0)
+    u0, v0 = u.clone(), v.clone()
+    sigma = torch.empty(1, device=DEV)
+    ops.spectral_norm(w, 24, 40, u, v, True, sigma)
+    v1 = F.normalize(w.t() @ u0, dim=0)
+    u1 = F.normalize(w @ v1, dim=0)
+    assert_parity(v, v1, 1e-5, "v")
+    assert_parity(u, u1, 1e-5, "u")
+    assert_parity(sigma.reshape(()), u1 @ (w @ v1), 1e-5, "sigma")
+    wr = w.clone().requires_grad_(True)
+    dwn = torch.randn_like(w)
+    ((wr / (u1 @ (wr @ v1))) * dwn).sum().backward()
+    dwo = torch.zeros_like(w)
+    ops.spectral_norm_bwd(dwn, w, u, v, sigma, 24, 40, dwo)
+    assert_parity(dwo, wr.grad, 1e-4, "sn bwd")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(64, 16, 16), (128, 8, 8), (24, 6, 10)])
+def test_gram_loss(dtype, C, H, W):
+    from multi_style_transfer_gan_b200 import ops
+    from oracle import restate as R
+    torch.manual_seed(7)
+    N = 2
+    f = q(torch.relu(torch.randn(N, C, H, W, device=DEV)), dtype).requires_grad_(True)
+    tgt = R.gram(torch.relu(torch.randn(N, C, H, W))).to(DEV)
+    ref_g = R.gram(f)
+    ref_l = ((ref_g - tgt) ** 2).mean()
+    ref_l.backward()
+    loss, g = ops.gram_loss_fwd(nhwc(f.detach(), dtype), tgt)
+    assert_parity(g, ref_g, 1e-4 if dtype == torch.float32 else 1e-2, "gram")
+    assert_parity(loss.reshape(()), ref_l, 1e-4 if dtype == torch.float32 else 2e-2, "loss")
+    df = ops.gram_loss_bwd(nhwc(f.detach(), dtype), g, tgt)
+    assert_parity(nchw(df), f.grad, 1e-4 if dtype == torch.float32 else 3e-2, "dfeat")
+
+
+def test_pooling_and_act_bwd():
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(8)
+    x = torch.randn(2, 8, 6, 10, device=DEV, requires_grad=True)
+    ref = F.max_pool2d(x, 2, 2)
+    y = ops.maxpool_fwd(nhwc(x.detach(), torch.float32))
+    assert torch.equal(nchw(y), ref)
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    dx = ops.maxpool_bwd(nhwc(x.detach(), torch.float32), nhwc(dy, torch.float32))
+    assert_parity(nchw(dx), x.grad, 1e-6, "maxpool bwd")
+    m = ops.avgpool_fwd(nhwc(x.detach(), torch.float32))
+    assert_parity(m, x.detach().mean((2, 3)), 1e-5, "avgpool")
