@@ -112,11 +112,15 @@ def require_device(index):
 # launch counter: every successful C-ABI call that launches kernels bumps this (bench.py's
 # gpu_launches claim is derived from it).
 launches = 0
+prof_hook = None   # set by profiler.start(): name -> end event to record after the launch
 
 
 def call(name, *args):
     global launches
+    end = prof_hook(name) if prof_hook is not None else None
     rc = getattr(load(), name)(*args)
+    if end is not None:
+        end.record()
     if rc != 0:
         check(rc)
     launches += 1

@@ -1,9 +1,370 @@
-// placeholder -- replaced by the tcgen05 implicit-GEMM kernel
+// tcgen05 / TMEM implicit-GEMM gather convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// One CTA computes a 128 (output pixels) x BN (output channels) tile:
+//   * warps 0-3 (128 threads, one im2col row each) gather the A operand straight from the NHWC
+//     activation with 16-byte cp.async (zero-fill for padding / K tail) into a 128B-swizzled,
+//     K-major shared-memory tile, and copy the matching [BN x 64] slab of the packed weights;
+//     a 3-stage mbarrier ring (full / empty) decouples them from the tensor core;
+//   * warp 4 allocates TMEM and its elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//     (UMMA 128 x BN x 16, A and B from shared-memory descriptors, D in TMEM), releasing each
+//     stage with tcgen05.commit;
+//   * after their last gather the same four warps become the epilogue: tcgen05.ld (32x32b) of their
+//     TMEM lane quarter, + bias, optional InstanceNorm statistics (per-column sums reduced by
+//     recursive halving over the warp, then across warps through smem, one fp64 atomic per channel
+//     per tile), activation, bf16 pack, 16-byte stores (or fp32 NCHW stores for the image).
+// Several CTAs are resident per SM (<= 97 KB smem, <= 128 TMEM columns each), so one CTA's epilogue
+// overlaps another's main loop.
+//
+// Same descriptor and semantics as the SIMT engine (conv_simt.cu); api.cu picks this path when
+// conv2d_tc_supported() holds.
 #include "common.cuh"
+
 namespace msg {
-bool conv2d_tc_supported(const msg_conv_desc*, const void*, const void*, const void*) { return false; }
-int conv2d_tc(const msg_conv_desc*, const void*, const void*, const float*, void*, double*, const double*, cudaStream_t) {
-  set_error("conv_tc: not built");
-  return MSG_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_STAGES = 3;
+constexpr int TC_LAG = TC_STAGES - 1;
+constexpr int TC_PRODUCERS = 128;
+constexpr int TC_THREADS = 160;
+constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset (8 rows x 128 B)
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// column sums over the 32 lanes of a warp by recursive halving: on return v[0] of lane l holds the
+// sum over all lanes of the original v[l].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = up ? v[i] : v[i + off];
+      float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+struct TcParams {
+  msg_conv_desc d;
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* w;
+  const float* bias;
+  void* y;
+  double* stats;
+  int BN;         // N tile (multiple of 16, <= 128)
+  int tmem_cols;  // power of two >= 32, >= BN
+  int K, nkb;
+  long long M;
+};
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const msg_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const int b_stage_bytes = BN * TC_BK * 2;
+  // carve: [A stages][B stages][barriers][tmem slot]   (base rounded up to 1024 B for SW128)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + TC_STAGES * A_STAGE_BYTES;
+  const uint32_t sBar = sB + TC_STAGES * b_stage_bytes;   // full[S], empty[S], accum
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + (sBar - base) + 8 * (2 * TC_STAGES + 1));
+  float* red = reinterpret_cast<float*>(gen_base);        // epilogue scratch aliases stage 0 of A
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (TC_STAGES + s); };
+  const uint32_t accum_bar = sBar + 8u * (2 * TC_STAGES);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+      mbar_init(accum_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long m0 = (long long)blockIdx.x * TC_BM;
+  const int co0 = blockIdx.y * BN;
+  const int hw = d.Hg * d.Wg;
+
+  if (warp < 4) {
+    // =============================== producer: im2col gather ===============================
+    const int row = tid;
+    const long long m = m0 + row;
+    const bool valid = m < p.M;
+    const long long mm = valid ? m : 0;
+    const int n = (int)(mm / hw);
+    const int rem = (int)(mm - (long long)n * hw);
+    const int gi = rem / d.Wg, gj = rem - gi * d.Wg;
+    const int ih0 = gi * d.in_stride - d.pad_h, iw0 = gj * d.in_stride - d.pad_w;
+    const __nv_bfloat16* xin = p.x + (size_t)n * d.Hi * d.Wi * d.Ci_total + d.ci_off;
+    const uint32_t a_row = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)row & 7u;
+    int th = 0, tw = 0, ci = 0;   // running (tap, channel) position of the next 8-element chunk
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      if (kb >= TC_STAGES) mbar_wait(empty_bar(s), ((kb / TC_STAGES) - 1) & 1);
+      const uint32_t a_base = sA + s * A_STAGE_BYTES + a_row;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ih = ih0 + th * d.dil, iw = iw0 + tw * d.dil;
+        const bool ok = valid && th < d.KH && ih >= 0 && ih < d.Hi && iw >= 0 && iw < d.Wi;
+        const __nv_bfloat16* src = ok ? xin + ((size_t)ih * d.Wi + iw) * d.Ci_total + ci : p.x;
+        cp_async16(a_base + (((uint32_t)j ^ sw) << 4), src, ok ? 16u : 0u);
+        ci += 8;
+        if (ci >= d.Cin) { ci = 0; if (++tw == d.KW) { tw = 0; ++th; } }
+      }
+      const uint32_t b_base = sB + s * b_stage_bytes;
+      const int k0 = kb * TC_BK;
+      for (int c = tid; c < BN * 8; c += TC_PRODUCERS) {
+        const int nr = c >> 3, j = c & 7;
+        const int kk = k0 + j * 8, co = co0 + nr;
+        const bool ok = co < d.Cout && kk < p.K;
+        const __nv_bfloat16* src = ok ? p.w + (size_t)co * p.K + kk : p.w;
+        cp_async16(b_base + (uint32_t)nr * 128u + (((uint32_t)j ^ ((uint32_t)nr & 7u)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (kb >= TC_LAG) {
+        cp_async_wait<TC_LAG>();
+        fence_proxy_async();
+        mbar_arrive(full_bar((kb - TC_LAG) % TC_STAGES));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (p.nkb > TC_LAG ? p.nkb - TC_LAG : 0); kb < p.nkb; ++kb) mbar_arrive(full_bar(kb % TC_STAGES));
+
+    // =============================== epilogue ===============================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool do_stats = d.flags & MSG_CONV_STATS;
+    const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
+    const bool accum = d.flags & MSG_CONV_ACCUM;
+    const int oh = gi * d.out_stride + d.out_off_h, ow = gj * d.out_stride + d.out_off_w;
+    const size_t opix = ((size_t)n * d.Ho + oh) * d.Wo + ow;
+    const bool vec_ok = ((d.Co_total | d.co_off) & 7) == 0;
+    const int cmax = (d.Cout - co0) < BN ? (d.Cout - co0) : BN;   // valid columns of this tile
+    for (int c0 = 0; c0 < cmax; c0 += 32) {
+      __syncwarp();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += (p.bias != nullptr && c0 + j < cmax) ? __ldg(p.bias + co0 + c0 + j) : 0.f;
+      }
+      if (do_stats) {   // dispatcher guarantees: every row valid and the whole tile in one image
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+        float cs = warp_transpose_reduce32(s1, lane);
+        float css = warp_transpose_reduce32(s2, lane);
+        red[(warp * 2 + 0) * 32 + lane] = cs;
+        red[(warp * 2 + 1) * 32 + lane] = css;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < 32) {
+          const int co = co0 + c0 + tid;
+          if (c0 + tid < cmax) {
+            float a = red[0 * 32 + tid] + red[2 * 32 + tid] + red[4 * 32 + tid] + red[6 * 32 + tid];
+            float b = red[1 * 32 + tid] + red[3 * 32 + tid] + red[5 * 32 + tid] + red[7 * 32 + tid];
+            double* st = p.stats + ((size_t)n * d.Co_total + d.co_off + co) * 2;
+            atomicAdd(st, (double)a);
+            atomicAdd(st + 1, (double)b);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (!valid) {
+        // nothing to store for rows past M (keep the warp converged for the next tcgen05.ld)
+      } else if (nchw) {
+        float* y = reinterpret_cast<float*>(p.y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = co0 + c0 + j;
+          if (c0 + j < cmax)
+            y[(((size_t)n * d.Co_total + d.co_off + co) * d.Ho + oh) * d.Wo + ow] = apply_act(v[j], d.act);
+        }
+      } else {
+        __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * d.Co_total + d.co_off + co0 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cl = c0 + g * 8;          // column within the tile
+          if (cl >= cmax) break;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+          if (vec_ok && cl + 7 < cmax) {
+            if (accum) {
+              float old[8];
+              unpack8(*reinterpret_cast<const uint4*>(y + g * 8), old);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += old[e];
+            }
+            *reinterpret_cast<uint4*>(y + g * 8) = pack8(o);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (cl + e < cmax) {
+                float val = accum ? o[e] + __bfloat162float(y[g * 8 + e]) : o[e];
+                y[g * 8 + e] = __float2bfloat16_rn(val);
+              }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(full_bar(s), (kb / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = make_sw128_desc(sA + s * A_STAGE_BYTES);
+        const uint64_t db = make_sw128_desc(sB + s * b_stage_bytes);
+#pragma unroll
+        for (int k4 = 0; k4 < TC_BK / 16; ++k4)   // +32 B per UMMA_K step inside the 128 B swizzle row
+          umma_bf16(tmem_base, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+inline int pick_bn(int Cout) {
+  int tiles = (Cout + 127) / 128;
+  int per = (Cout + tiles - 1) / tiles;
+  int bn = (per + 15) / 16 * 16;
+  return bn < 16 ? 16 : bn;
+}
+inline size_t tc_smem_bytes(int BN) {
+  return (size_t)TC_STAGES * (A_STAGE_BYTES + BN * TC_BK * 2) + 8 * (2 * TC_STAGES + 1) + 16 + 1024;
+}
+
+}  // namespace
+
+bool conv2d_tc_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y) {
+  if (d->dtype != MSG_BF16) return false;
+  if (d->flags & MSG_CONV_IN_NORM) return false;
+  if ((d->Cin | d->Ci_total | d->ci_off) & 7) return false;
+  if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
+  const long long hw = (long long)d->Hg * d->Wg;
+  if ((d->flags & MSG_CONV_STATS) && (hw % TC_BM) != 0) return false;
+  if (!(d->flags & MSG_CONV_OUT_NCHW_F32) && ((uintptr_t)y & 15)) return false;
+  if ((d->flags & MSG_CONV_OUT_NCHW_F32) && d->Cout > 128) return false;
+  return true;
+}
+
+int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+              double* stats, const double* in_stats, cudaStream_t st) {
+  (void)in_stats;
+  TcParams p;
+  p.d = *d;
+  p.x = (const __nv_bfloat16*)x;
+  p.w = (const __nv_bfloat16*)w;
+  p.bias = bias;
+  p.y = y;
+  p.stats = stats;
+  p.BN = pick_bn(d->Cout);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  p.K = d->KH * d->KW * d->Cin;
+  p.nkb = (p.K + TC_BK - 1) / TC_BK;
+  p.M = (long long)d->N * d->Hg * d->Wg;
+  const size_t smem = tc_smem_bytes(p.BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((p.M + TC_BM - 1) / TC_BM), (unsigned)((d->Cout + p.BN - 1) / p.BN));
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  return check_launch("conv_tc_kernel");
+}
+
 }  // namespace msg

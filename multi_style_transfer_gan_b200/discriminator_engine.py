@@ -15,9 +15,9 @@ D_CONVS = ("main.0", "main.2", "main.5", "main.8", "batch_head.0", "structure_he
 class DiscriminatorEngine:
     def __init__(self, channels):
         c = self.c = channels
-        self.cin_pad = 4
         g = self.geom = {}
-        g["main.0"] = ConvGeom("conv", self.cin_pad, c, 4, 2, 1)
+        g["main.0@4"] = ConvGeom("conv", 4, c, 4, 2, 1)     # image 3 -> 4 channels (fp32)
+        g["main.0@8"] = ConvGeom("conv", 8, c, 4, 2, 1)     # image 3 -> 8 channels (bf16 / tcgen05)
         g["main.2"] = ConvGeom("conv", c, 2 * c, 4, 2, 1)
         g["main.5"] = ConvGeom("conv", 2 * c, 4 * c, 4, 2, 1)
         g["main.8"] = ConvGeom("conv", 4 * c, 8 * c, 4, 2, 1)
@@ -25,9 +25,16 @@ class DiscriminatorEngine:
         g["structure_head.0"] = ConvGeom("conv", 8 * c, 8 * c, 3, 1, 1)
         g["structure_head.3"] = ConvGeom("conv", 8 * c, 1, 4, 1, 1)
 
-    def _master(self, w, name):
-        if name == "main.0" and w.shape[1] != self.cin_pad:
-            w = F.pad(w, [0, 0, 0, 0, 0, self.cin_pad - w.shape[1]])
+    @staticmethod
+    def cin_pad(dtype):
+        return 4 if dtype == torch.float32 else 8
+
+    def _g(self, name, dtype):
+        return self.geom[f"main.0@{self.cin_pad(dtype)}"] if name == "main.0" else self.geom[name]
+
+    def _master(self, w, name, dtype):
+        if name == "main.0":
+            w = F.pad(w, [0, 0, 0, 0, 0, self.cin_pad(dtype) - w.shape[1]])
         return w.contiguous()
 
     def _sigma(self, P, name, training):
@@ -43,19 +50,19 @@ class DiscriminatorEngine:
     def forward(self, P, x, dtype, training, save):
         """x: fp32 NCHW [N,3,H,W] -> (score_map fp32 [N] (plane mean of the batch head),
         struct fp32 [N,1,h,w], saved)."""
-        g = self.geom
+        g = {n: self._g(n, dtype) for n in D_CONVS}
         N, Cx, H, W = x.shape
         if Cx != 3 or H % 16 or W % 16 or H < 32 or W < 32:
             raise RuntimeError(f"EnhancedDiscriminator: expected [N,3,H,W] with H,W multiples of 16 and >= 32, got {tuple(x.shape)}")
         sn = {n: self._sigma(P, n, training) for n in D_CONVS}
 
         def wp(n):
-            return g[n].pack_fwd(self._master(P[f"{n}.weight_orig"].detach(), n), dtype, sn[n][0])
+            return g[n].pack_fwd(self._master(P[f"{n}.weight_orig"].detach(), n, dtype), dtype, sn[n][0])
 
         def bias(n):
             return P[f"{n}.bias"].detach().contiguous()
 
-        x0 = ops.nchw_to_nhwc(x, dtype, self.cin_pad)
+        x0 = ops.nchw_to_nhwc(x, dtype, self.cin_pad(dtype))
         h1 = g["main.0"].forward(x0, wp("main.0"), bias("main.0"), act=ACT_LRELU)
         acts = {"x0": x0, "h1": h1}
         a = h1
@@ -82,7 +89,7 @@ class DiscriminatorEngine:
     def backward(self, P, saved, dscore, dstruct, dtype, need_dx, need_dw):
         """dscore fp32 [N], dstruct fp32 [N,1,h,w] (either may be None).  Returns (dx NCHW | None,
         grads {state_dict key: fp32})."""
-        g, acts, sn = self.geom, saved["acts"], saved["sn"]
+        g, acts, sn = {n: self._g(n, dtype) for n in D_CONVS}, saved["acts"], saved["sn"]
         G = {}
 
         def conv_bwd(n, x, dy, need_dx=True):
@@ -90,7 +97,7 @@ class DiscriminatorEngine:
             w_orig = P[f"{n}.weight_orig"].detach()
             sigma, u, v = sn[n]
             if need_dw:
-                m = self._master(w_orig, n)
+                m = self._master(w_orig, n, dtype)
                 dw = torch.zeros_like(m)
                 db = torch.zeros(geom.Cout, device=m.device, dtype=torch.float32)
                 geom.wgrad(x, dy, dw, db)
@@ -103,7 +110,7 @@ class DiscriminatorEngine:
                 G[f"{n}.bias"] = db
             if not need_dx:
                 return None
-            wpd = geom.pack_dgrad(self._master(w_orig, n), dtype, sigma)
+            wpd = geom.pack_dgrad(self._master(w_orig, n, dtype), dtype, sigma)
             return geom.dgrad(dy, wpd, x.shape[1:3])
 
         feat = acts["feat"]

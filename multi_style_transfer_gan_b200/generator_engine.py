@@ -33,12 +33,14 @@ class GeneratorEngine:
         c = self.c = channels
         if c % 4:
             raise ValueError("EnhancedGenerator: channels must be a multiple of 4 (MultiScaleBlock splits C/4)")
-        self.cin_pad = 4      # image channels 3 -> 4 (zero weights for the pad channel)
-        self.cout_pad = 4     # output conv 3 -> 4 filters (4th is zero, never stored)
+        # image channels 3 -> 4 (fp32) / 8 (bf16: the tcgen05 gather moves 16-byte chunks), with zero
+        # weights for the pad channels; output conv 3 -> 4 / 8 filters (extra ones zero, never stored)
         self.width = {"down1": 2 * c, "down2": 4 * c, "up1": 2 * c, "up2": c}
         self.inwidth = {"down1": c, "down2": 2 * c, "up1": 4 * c, "up2": 2 * c}
         g = self.geom = {}
-        g["initial.0"] = ConvGeom("conv", self.cin_pad, c, 7, 1, 3)
+        for pad in (4, 8):
+            g[f"initial.0@{pad}"] = ConvGeom("conv", pad, c, 7, 1, 3)
+            g[f"output.0@{pad}"] = ConvGeom("conv", c, pad, 7, 1, 3)
         for s in STAGES:
             C, Ci = self.width[s], self.inwidth[s]
             g[f"{s}.0"] = ConvGeom("convT" if s.startswith("up") else "conv", Ci, C, 4, 2, 1)
@@ -47,19 +49,27 @@ class GeneratorEngine:
             for i, (k, p, d) in enumerate(BRANCHES, start=1):
                 g[f"{s}.4.branch{i}.0"] = ConvGeom("conv", C, C // 4, k, 1, p, d)
             g[f"{s}.4.fusion.0"] = ConvGeom("conv", C, C, 1)
-        g["output.0"] = ConvGeom("conv", c, self.cout_pad, 7, 1, 3)
         self._cache = {}
+
+    @staticmethod
+    def edge_pad(dtype):
+        return 4 if dtype == torch.float32 else 8
+
+    def _g(self, name, dtype):
+        if name in ("initial.0", "output.0"):
+            return self.geom[f"{name}@{self.edge_pad(dtype)}"]
+        return self.geom[name]
 
     # ---- packed-weight cache ---------------------------------------------------------------------
     def invalidate(self):
         self._cache.clear()
 
-    def _master(self, params, name):
+    def _master(self, params, name, dtype):
         w = params[f"{name}.weight"]
         if name == "initial.0":
-            w = _pad_dim(w, 1, self.cin_pad)
+            w = _pad_dim(w, 1, self.edge_pad(dtype))
         elif name == "output.0":
-            w = _pad_dim(w, 0, self.cout_pad)
+            w = _pad_dim(w, 0, self.edge_pad(dtype))
         return w.contiguous()
 
     def _packed(self, params, name, which, dtype):
@@ -69,40 +79,48 @@ class GeneratorEngine:
         hit = self._cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        m = self._master(params, name)
-        g = self.geom[name]
+        m = self._master(params, name, dtype)
+        g = self._g(name, dtype)
         t = g.pack_fwd(m, dtype) if which == "fwd" else g.pack_dgrad(m, dtype)
         self._cache[key] = (ver, t)
         return t
 
-    def _bias(self, params, name):
+    def _bias(self, params, name, dtype=None):
         b = params[f"{name}.bias"]
         if name == "output.0":
-            b = _pad_dim(b, 0, self.cout_pad)
+            b = _pad_dim(b, 0, self.edge_pad(dtype))
         return b.contiguous()
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _stage_fwd(self, P, s, a_in, dtype):
+    def _stage_fwd(self, P, s, a_in, dtype, keep=True):
+        """keep=False (inference): intermediates are dropped as soon as their consumer has been
+        launched, so the caching allocator recycles them within the stage."""
         g = self.geom
         C = self.width[s]
         N = a_in.shape[0]
         dev = a_in.device
         st0 = ops.new_stats(N, C, dev)
         y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
-        a0 = ops.instnorm_apply(y0, st0, ACT_RELU)
+        a0 = ops.instnorm_apply(y0, st0, ACT_RELU, out=None if keep else y0)
         qkv = g[f"{s}.3.qkv"].forward(a0, self._packed(P, f"{s}.3.qkv", "fwd", dtype), self._bias(P, f"{s}.3.qkv"))
         att = ops.local_attn_fwd(qkv)
+        if not keep:
+            del y0, a0, qkv
         a1 = g[f"{s}.3.proj"].forward(att, self._packed(P, f"{s}.3.proj", "fwd", dtype), self._bias(P, f"{s}.3.proj"))
+        if not keep:
+            del att
         b = torch.empty_like(a1)
         stb = ops.new_stats(N, C, dev)
         for i in range(1, 5):
             n = f"{s}.4.branch{i}.0"
             g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
-        bn = ops.instnorm_apply(b, stb, ACT_RELU)
+        bn = ops.instnorm_apply(b, stb, ACT_RELU, out=None if keep else b)
         stf = ops.new_stats(N, C, dev)
         n = f"{s}.4.fusion.0"
         f = g[n].forward(bn, self._packed(P, n, "fwd", dtype), self._bias(P, n), stats=stf)
-        a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1)
+        a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1, out=None if keep else f)
+        if not keep:
+            return a2, None
         saved = dict(a_in=a_in, y0=y0, st0=st0, a0=a0, qkv=qkv, att=att, a1=a1, b=b, stb=stb, bn=bn, f=f, stf=stf)
         return a2, saved
 
@@ -115,28 +133,30 @@ class GeneratorEngine:
             # the reference's LocalAttention pad path is broken (enhanced_generator.py:15-23): such
             # sizes raise there too.
             raise RuntimeError(f"EnhancedGenerator: H and W must be multiples of 16, got {H}x{W}")
-        x0 = ops.nchw_to_nhwc(x, dtype, self.cin_pad)
+        x0 = ops.nchw_to_nhwc(x, dtype, self.edge_pad(dtype))
         sti = ops.new_stats(N, self.c, x.device)
-        yi = self.geom["initial.0"].forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
-        a = ops.instnorm_apply(yi, sti, ACT_RELU)
-        saved = {"x0": x0, "yi": yi, "sti": sti, "ai": a} if save else None
+        yi = self._g("initial.0", dtype).forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
+        a = ops.instnorm_apply(yi, sti, ACT_RELU, out=None if save else yi)
+        saved = {"x0": x0, "yi": yi, "sti": sti} if save else None
         for s in ("down1", "down2"):
-            a, sv = self._stage_fwd(P, s, a, dtype)
+            a_in = a
+            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"))
             if save:
-                saved[s] = sv if save == "full" else {"a_in": sv["a_in"]}
+                saved[s] = sv if save == "full" else {"a_in": a_in}
         return a, saved
 
     def decode(self, P, a, dtype, save):
         """a: [N,H/4,W/4,4c] NHWC -> (y fp32 NCHW in [-1,1], saved)."""
         saved = {} if save else None
         for s in ("up1", "up2"):
-            a, sv = self._stage_fwd(P, s, a, dtype)
+            a_in = a
+            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"))
             if save:
-                saved[s] = sv if save == "full" else {"a_in": sv["a_in"]}
+                saved[s] = sv if save == "full" else {"a_in": a_in}
         N, H, W, _ = a.shape
         y = torch.empty((N, 3, H, W), device=a.device, dtype=torch.float32)
         go = ConvGeom("conv", self.c, 3, 7, 1, 3)   # store 3 filters of the 4-row packed weight
-        go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0"), act=ACT_TANH, nchw_out=y)
+        go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0", dtype), act=ACT_TANH, nchw_out=y)
         if save:
             saved["a_last"] = a
             saved["y"] = y
@@ -145,8 +165,8 @@ class GeneratorEngine:
     # ---- backward --------------------------------------------------------------------------------
     def _conv_bwd(self, P, G, name, x, dy, dtype, need_dx=True, in_hw=None, dy_c_off=0, dx_out=None, accumulate=False):
         """Accumulates weight / bias grads of conv `name` into G and returns dx (or None)."""
-        g = self.geom[name]
-        m = self._master(P, name)
+        g = self._g(name, dtype)
+        m = self._master(P, name, dtype)
         dw = torch.zeros_like(m)
         db = torch.zeros(m.shape[1] if g.kind == "convT" else m.shape[0], device=m.device, dtype=torch.float32)
         g.wgrad(x, dy, dw, db, dy_c_off=dy_c_off)
@@ -163,7 +183,7 @@ class GeneratorEngine:
 
     def _stage_bwd(self, P, G, s, sv, da2, dtype):
         if "y0" not in sv:  # checkpointed: recompute the stage from its input (enhanced_generator.py:186-208)
-            _, sv = self._stage_fwd(P, s, sv["a_in"], dtype)
+            _, sv = self._stage_fwd(P, s, sv["a_in"], dtype, keep=True)
         C = self.width[s]
         df = ops.instnorm_bwd(sv["f"], sv["stf"], da2, ACT_RELU)
         dbn = self._conv_bwd(P, G, f"{s}.4.fusion.0", sv["bn"], df, dtype)
@@ -180,7 +200,7 @@ class GeneratorEngine:
 
     def decode_bwd(self, P, G, saved, dy, dtype):
         """dy: fp32 NCHW grad of the image.  Returns d(a) at the decoder input (NHWC)."""
-        dz = ops.tanh_bwd_nchw(saved["y"], dy, dtype, self.cout_pad)
+        dz = ops.tanh_bwd_nchw(saved["y"], dy, dtype, self.edge_pad(dtype))
         da = self._conv_bwd(P, G, "output.0", saved["a_last"], dz, dtype)
         for s in ("up2", "up1"):
             da = self._stage_bwd(P, G, s, saved[s], da, dtype)

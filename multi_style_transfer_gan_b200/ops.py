@@ -270,7 +270,7 @@ def nhwc_to_nchw(x, C=None):
     return y
 
 
-def blend_outputs(ys, w, x=None, w_x=0.0, gain=1.0, clip=None, out_uint8=False):
+def blend_outputs(ys, w, x=None, w_x=0.0, gain=1.0, clip=None, out_uint8=False, out=None):
     """out = gain * (sum_s w[s]*ys[s] + w_x*x), optional clip; optionally also the uint8 image
     ((v+1)/2 -> clamp -> *255).  ys: list of fp32 CUDA tensors of identical shape."""
     ys = [y.detach().contiguous() for y in ys]
@@ -279,12 +279,20 @@ def blend_outputs(ys, w, x=None, w_x=0.0, gain=1.0, clip=None, out_uint8=False):
     assert S == len(w)
     ptrs = (ctypes.c_void_p * S)(*[y.data_ptr() for y in ys])
     ws = (ctypes.c_float * S)(*[float(v) for v in w])
-    out = torch.empty_like(ys[0])
-    u8 = torch.empty(ys[0].shape, device=ys[0].device, dtype=torch.uint8) if out_uint8 else None
+    if out is not None and out.dtype == torch.uint8:
+        u8, out = out, None
+        assert u8.is_contiguous() and u8.shape == ys[0].shape
+    else:
+        if out is None:
+            out = torch.empty_like(ys[0])
+        assert out.is_contiguous() and out.shape == ys[0].shape and out.dtype == torch.float32
+        u8 = torch.empty(ys[0].shape, device=ys[0].device, dtype=torch.uint8) if out_uint8 else None
     lo, hi = (clip if clip is not None else (0.0, 0.0))
     xx = None if x is None else x.detach().contiguous()
     _lib.call("msg_blend_outputs", ptrs, ws, S, _p(xx), float(w_x), float(gain), int(clip is not None),
-              float(lo), float(hi), out.numel(), _p(out), _p(u8), _stream())
+              float(lo), float(hi), ys[0].numel(), _p(out), _p(u8), _stream())
+    if out is None:
+        return u8
     return (out, u8) if out_uint8 else out
 
 

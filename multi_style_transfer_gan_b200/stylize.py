@@ -1,0 +1,86 @@
+"""Batch multi-style stylisation: the reference's per-file loop (batch_process_images.py:498-531 --
+one image per iteration, B=1) and its output-space style blends (advanced_transform.py:206-213,
+direct_transform.py:155-165, batch_process_images.py:306-309) as ONE batched device pipeline.
+
+"Multi-style with adjustable weights" in the reference is a linear blend of generator outputs
+(SURVEY.md F4):  out = gain * (sum_s w_s * G_s(x) + w_x * x).  Each style s is one generator
+(one state_dict).  Images are independent (InstanceNorm is per-sample, LocalAttention per-window),
+so a batch is sharded by image across GPUs with no communication (shard_range below).
+
+The batch is walked in micro-batches sized for the 126 MB L2 so that each kernel's output is still
+L2-resident when the next kernel reads it; host input is staged through pinned memory on a copy
+stream so H2D of micro-batch i+1 overlaps the compute of micro-batch i.
+"""
+import torch
+
+from . import ops
+
+
+def shard_range(num_images, rank, world_size):
+    """Contiguous shard [lo, hi) of `num_images` images for `rank` (no communication needed)."""
+    per = (num_images + world_size - 1) // world_size
+    lo = min(rank * per, num_images)
+    return lo, min(lo + per, num_images)
+
+
+class MultiStyleStylizer:
+    def __init__(self, generators, precision="bf16", micro_batch=4):
+        if not generators:
+            raise ValueError("need at least one generator (one per style)")
+        self.generators = list(generators)
+        for g in self.generators:
+            g.eval()
+            g.set_precision(precision)
+        self.micro_batch = int(micro_batch)
+        self.device = next(self.generators[0].parameters()).device
+        self._copy_stream = None
+
+    @torch.no_grad()
+    def __call__(self, x, weights, w_x=0.0, gain=1.0, clip=None, out_uint8=False, out=None):
+        """x: float32 [B,3,H,W] in [-1,1], on the device or on the host (pinned for overlap).
+        Returns the blended fp32 images [B,3,H,W] on the device, or -- with out_uint8=True -- the
+        uint8 images ((v+1)/2 -> clamp -> *255, direct_transform.py:66-71) in `out` (host or device
+        uint8 tensor [B,3,H,W]; allocated on the device if None)."""
+        S = len(self.generators)
+        if len(weights) != S:
+            raise ValueError(f"{S} styles but {len(weights)} weights")
+        B = x.shape[0]
+        mb = self.micro_batch
+        host_in = not x.is_cuda
+        if out is None:
+            out = torch.empty((B, 3) + tuple(x.shape[2:]), device=self.device,
+                              dtype=torch.uint8 if out_uint8 else torch.float32)
+        host_out = not out.is_cuda
+        cur = torch.cuda.current_stream(self.device)
+        if host_in and self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        chunks = [(lo, min(lo + mb, B)) for lo in range(0, B, mb)]
+        staged = {}
+
+        def stage(i):
+            lo, hi = chunks[i]
+            if not host_in:
+                staged[i] = (x[lo:hi], None)
+                return
+            with torch.cuda.stream(self._copy_stream):
+                t = x[lo:hi].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            staged[i] = (t, ev)
+
+        stage(0)
+        for i, (lo, hi) in enumerate(chunks):
+            if i + 1 < len(chunks):
+                stage(i + 1)
+            xi, ev = staged.pop(i)
+            if ev is not None:
+                cur.wait_event(ev)
+                xi.record_stream(cur)
+            ys = [g(xi) for g in self.generators]
+            dst = None if host_out else out[lo:hi]      # device result: the blend writes it in place
+            if dst is None:
+                dst = torch.empty(ys[0].shape, device=self.device, dtype=out.dtype)
+            ops.blend_outputs(ys, weights, x=xi if w_x != 0.0 else None, w_x=w_x, gain=gain, clip=clip, out=dst)
+            if host_out:
+                out[lo:hi].copy_(dst, non_blocking=True)
+        return out

@@ -1,0 +1,87 @@
+"""tcgen05 implicit-GEMM conv (conv_tc.cu) against the SIMT engine (conv_simt.cu) and against
+PyTorch fp32, on the layer shapes of the c=64 generator (scaled-down planes)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def nhwc(x, dtype=torch.bfloat16):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+LAYERS = [
+    # kind, Cin, Cout, k, s, p, d, H, W   (c=64 generator layers)
+    ("conv", 8, 64, 7, 1, 3, 1, 64, 64),      # initial (image padded to 8 channels)
+    ("conv", 64, 128, 4, 2, 1, 1, 64, 64),    # down1.0
+    ("conv", 128, 256, 4, 2, 1, 1, 32, 32),   # down2.0
+    ("conv", 128, 384, 1, 1, 0, 1, 32, 32),   # qkv
+    ("conv", 64, 192, 1, 1, 0, 1, 64, 64),    # qkv (C=64): BN=96 tiles
+    ("conv", 256, 256, 1, 1, 0, 1, 16, 16),   # proj / fusion
+    ("conv", 256, 64, 3, 1, 1, 1, 16, 16),    # branch2
+    ("conv", 128, 32, 3, 1, 2, 2, 32, 32),    # branch3
+    ("conv", 64, 16, 3, 1, 4, 4, 64, 64),     # branch4 (N=16)
+    ("convT", 256, 128, 4, 2, 1, 1, 16, 16),  # up1.0
+    ("convT", 128, 64, 4, 2, 1, 1, 32, 32),   # up2.0
+    ("conv", 64, 8, 7, 1, 3, 1, 64, 64),      # output (padded filters)
+    ("conv", 64, 128, 4, 2, 1, 1, 48, 80),    # plane not a multiple of 128 -> partial tiles
+]
+
+
+@pytest.mark.parametrize("case", LAYERS, ids=lambda c: "-".join(map(str, c)))
+def test_tc_vs_simt_and_torch(case):
+    from multi_style_transfer_gan_b200 import ops
+    kind, Cin, Cout, k, s, p, d, H, W = case
+    torch.manual_seed(0)
+    g = ops.ConvGeom(kind, Cin, Cout, k, s, p, d)
+    N = 2
+    dt = torch.bfloat16
+    x = (torch.randn(N, Cin, H, W, device=DEV)).to(dt).float()
+    w = (torch.randn(*g.weight_shape(), device=DEV) * (1.0 / (Cin * k * k) ** 0.5)).to(dt).float()
+    b = torch.randn(Cout, device=DEV)
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=1) if kind == "convT" else F.conv2d(x, w, b, stride=s, padding=p, dilation=d)
+    wp = g.pack_fwd(w.contiguous(), dt)
+    xh = nhwc(x)
+    Ho, Wo = g.out_hw(H, W)
+    use_stats = (H * W if kind == "convT" else Ho * Wo) % 128 == 0
+    st_tc = ops.new_stats(N, Cout, DEV) if use_stats else None
+    st_si = ops.new_stats(N, Cout, DEV) if use_stats else None
+    y_tc = g.forward(xh, wp, b, stats=st_tc)
+    y_si = g.forward(xh, wp, b, stats=st_si, extra_flags=ops.CONV_FORCE_SIMT)
+    assert_parity(nchw(y_tc), ref, 1e-2, "tc vs torch")
+    assert_parity(nchw(y_tc), nchw(y_si), 1e-2, "tc vs simt")
+    if use_stats:
+        assert_parity(st_tc, st_si, 1e-4, "stats tc vs simt")
+    # fused activation epilogues
+    y_act = g.forward(xh, wp, b, act=ops.ACT_LRELU)
+    assert_parity(nchw(y_act), F.leaky_relu(ref, 0.2), 1e-2, "lrelu epilogue")
+
+
+def test_tc_nchw_tanh_epilogue_and_accumulate():
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(1)
+    dt = torch.bfloat16
+    N, C, H, W = 2, 64, 32, 32
+    x = torch.randn(N, C, H, W, device=DEV).to(dt).float()
+    w = (torch.randn(4, C, 7, 7, device=DEV) * 0.02).to(dt).float()
+    w[3] = 0
+    b = torch.randn(4, device=DEV)
+    g = ops.ConvGeom("conv", C, 3, 7, 1, 3)
+    y = torch.empty(N, 3, H, W, device=DEV)
+    g.forward(nhwc(x), ops.pack_weight(w, ops.PACK_FWD, dt), b, act=ops.ACT_TANH, nchw_out=y)
+    assert_parity(y, torch.tanh(F.conv2d(x, w[:3], b[:3], padding=3)), 1e-2, "nchw tanh")
+    # accumulate flag: y += conv
+    g2 = ops.ConvGeom("conv", C, 32, 3, 1, 1)
+    w2 = (torch.randn(32, C, 3, 3, device=DEV) * 0.05).to(dt).float()
+    base = torch.randn(N, 32, H, W, device=DEV).to(dt)
+    out = nhwc(base.float())
+    g2.forward(nhwc(x), g2.pack_fwd(w2, dt), None, out=out, extra_flags=ops.CONV_ACCUM)
+    assert_parity(nchw(out), base.float() + F.conv2d(x, w2, None, padding=1), 1e-2, "accumulate")

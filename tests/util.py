@@ -19,8 +19,10 @@ def parity_errors(a, b):
             float(d.norm()) / (nrm if nrm > 0 else 1.0))
 
 
-def assert_parity(a, b, rel=1e-4, name="", floor=0.0):
-    """floor: absolute error allowed in addition (for quantities that are ~0 by construction)."""
+def assert_parity(a, b, rel=1e-4, name="", floor=0.0, max_rel=None):
+    """floor: absolute error allowed in addition (for quantities that are ~0 by construction).
+    max_rel: separate bound for the normalised max error (default: rel)."""
+    max_rel = rel if max_rel is None else max_rel
     assert a.shape == b.shape, f"{name}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
@@ -29,6 +31,6 @@ def assert_parity(a, b, rel=1e-4, name="", floor=0.0):
     scale = float(b.abs().max())
     emax = float(d.max()) if d.numel() else 0.0
     el2 = float((a - b).norm())
-    assert emax <= rel * scale + floor, f"{name}: max|a-b|={emax:.3e} > {rel:g}*max|b|={rel*scale:.3e} (+{floor:g})"
+    assert emax <= max_rel * scale + floor, f"{name}: max|a-b|={emax:.3e} > {max_rel:g}*max|b|={max_rel*scale:.3e} (+{floor:g})"
     assert el2 <= rel * float(b.norm()) + floor * d.numel() ** 0.5, \
         f"{name}: rel-L2 {el2/float(b.norm()+1e-300):.3e} > {rel:g}"
