@@ -45,6 +45,9 @@ int sm_count() { return dev_info().sms; }
 int conv_validate(const msg_conv_desc* d);
 int conv2d_simt(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                 double* stats, const double* in_stats, cudaStream_t st);
+bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
+int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+               double* stats, cudaStream_t st);
 bool conv2d_tc_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
 int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
               double* stats, const double* in_stats, cudaStream_t st);
@@ -55,8 +58,12 @@ int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const 
   if (rc) return rc;
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_STATS without a stats buffer");
   MSG_REQUIRE(!(d->flags & MSG_CONV_IN_NORM) || in_stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_IN_NORM without in_stats");
-  if (!(d->flags & MSG_CONV_FORCE_SIMT) && conv2d_tc_supported(d, x, w, y))
-    return conv2d_tc(d, x, w, bias, y, stats, in_stats, st);
+  if (!(d->flags & MSG_CONV_FORCE_SIMT)) {
+    if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_tma_supported(d, x, w, y))
+      return conv2d_tma(d, x, w, bias, y, stats, st);            // persistent TMA + tcgen05 kernel
+    if (conv2d_tc_supported(d, x, w, y))
+      return conv2d_tc(d, x, w, bias, y, stats, in_stats, st);   // cp.async gather + tcgen05 kernel
+  }
   return conv2d_simt(d, x, w, bias, y, stats, in_stats, st);
 }
 

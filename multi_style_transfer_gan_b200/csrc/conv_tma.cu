@@ -1,0 +1,509 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM convolution fed by TMA (sm_100a, bf16).
+//
+// The A operand of an implicit-GEMM conv on NHWC data needs no im2col buffer and no per-thread
+// address math when the output plane width is a power of two: a 128-pixel M tile is R = 128/Wt full
+// (or partial, Wt = 128) output rows of Wt pixels, and for one filter tap its input pixels form a
+// regular 4-D box [64 channels x Wt pixels (step = conv stride) x R rows (step = stride) x 1 image]
+// of the activation tensor.  ONE cp.async.bulk.tensor.4d (tile mode, 128B swizzle, hardware
+// zero-fill outside the image = the conv's zero padding, negative start coordinates allowed) lands it
+// in shared memory in exactly the K-major SWIZZLE_128B layout tcgen05.mma reads.  The weight slab of
+// the same K block is one 2-D TMA box.  So the producer is a single thread issuing two TMA
+// instructions per K block; the SM's issue slots are free for the epilogue.
+//
+//   warp 0 : TMA producer (one elected lane), ring of kStages smem stages, full/empty mbarriers
+//   warp 1 : TMEM allocator + MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128,
+//            N=BN<=256, K=16, accumulators DOUBLE-BUFFERED in TMEM (2 x BN columns)
+//   warps 2-5 : epilogue.  tcgen05.ld -> +bias -> (IN statistics) -> activation -> bf16 -> smem
+//            staging -> coalesced 128-byte row stores; releases the accumulator buffer as soon as it
+//            has been read, so the next tile's MMAs overlap this tile's stores.
+// One CTA per SM, looping over (m tile, n tile) work items.
+//
+// Geometry requirement (checked by conv2d_tma_supported): Cin % 64 == 0, and either Wg % 128 == 0 or
+// (128 % Wg == 0 and Hg % (128/Wg) == 0).  Everything else takes the gather kernel (conv_tc.cu) or
+// the SIMT engine.  Same descriptor semantics as include/msg_b200.h.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace msg {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NTHREADS = 192;
+constexpr int STAGE_PITCH = 128 + 16;   // manual flush: 64 bf16 columns per row + 16 B skew
+constexpr int STAGE_BYTES = 2 * BM * 128;   // two [128 rows x 64 cols] bf16 TMA-store buffers (SW128)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = up ? v[i] : v[i + off];
+      float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+struct TmaParams {
+  msg_conv_desc d;
+  const float* bias;
+  void* y;
+  double* stats;
+  int BN, n_tiles, m_tiles, stages, tmem_cols;
+  int Wt, R;            // M tile = R rows x Wt pixels
+  int cblocks;          // Cin / 64
+  int nkb;              // KH*KW*cblocks
+  int tstore;           // output rows of a tile are 128 consecutive pixels: full 64-column groups go out by TMA
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapC, const TmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const msg_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN, S = p.stages;
+  const int b_bytes = BN * BK * 2;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base;
+  const uint32_t sB = sA + S * A_BYTES;
+  const uint32_t sStage = sB + S * b_bytes;                 // epilogue staging, 1024-byte aligned
+  const uint32_t sRed = sStage + STAGE_BYTES;               // 8 x 32 floats
+  const uint32_t sBar = sRed + 1024;                        // full[S], empty[S], tfull[2], tempty[2]
+  uint8_t* stage_gen = gen + (sStage - base);
+  float* red = reinterpret_cast<float*>(gen + (sRed - base));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return sBar + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return sBar + 8u * (2 * S + 2 + b); };
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int tiles_per_row = d.Wg / p.Wt;        // >= 1
+  const int tile_rows = d.Hg / p.R;             // row groups per image
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int img = mt / (tile_rows * tiles_per_row);
+        const int rem = mt - img * (tile_rows * tiles_per_row);
+        const int rg = rem / tiles_per_row, cg = rem - rg * tiles_per_row;
+        const int i0 = rg * p.R, j0 = cg * p.Wt;
+        const int w_base = j0 * d.in_stride - d.pad_w, h_base = i0 * d.in_stride - d.pad_h;
+        int kb = 0;
+        for (int th = 0; th < d.KH; ++th)
+          for (int tw = 0; tw < d.KW; ++tw)
+            for (int cb = 0; cb < p.cblocks; ++cb, ++kb, ++it) {
+              const int s = it % S;
+              if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+              mbar_expect_tx(full_bar(s), A_BYTES + b_bytes);
+              tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), cb * BK, w_base + tw * d.dil, h_base + th * d.dil, img);
+              tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(sA + s * A_BYTES);
+          const uint64_t db = make_sw128_desc(sB + s * b_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4)
+            umma_bf16(tacc, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ===================================== epilogue (warps 2-5) =====================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // row of the M tile
+    const bool do_stats = d.flags & MSG_CONV_STATS;
+    const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
+    const bool accum = d.flags & MSG_CONV_ACCUM;
+    const int hw = d.Hg * d.Wg;
+    uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);   // manual-flush slice of this warp
+    const int etid = tid - 64;                    // 0..127 within the epilogue group
+    uint32_t lt = 0, sgrp = 0;                    // tiles done, TMA-store groups issued
+    bool tma_pending = false;                     // (thread etid==0) bulk groups possibly still reading smem
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int buf = lt & 1;
+      const long long m0 = (long long)mt * BM;
+      const int co0 = nt * BN;
+      const int cmax = (d.Cout - co0) < BN ? (d.Cout - co0) : BN;
+      const bool vec = !nchw && ((d.Co_total | d.co_off | cmax) & 7) == 0;
+      int opix;
+      {
+        const long long m = m0 + row;
+        const int n = (int)(m / hw);
+        const int rem = (int)(m - (long long)n * hw);
+        const int gi = rem / d.Wg, gj = rem - gi * d.Wg;
+        opix = (n * d.Ho + gi * d.out_stride + d.out_off_h) * d.Wo + gj * d.out_stride + d.out_off_w;
+      }
+      const int opix0 = __shfl_sync(0xffffffffu, opix, 0) - q * 32;   // tstore: rows are consecutive pixels
+      const int n_img = (int)(m0 / hw);
+      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+      for (int cg = 0; cg < cmax; cg += 64) {
+        const int ncol = (cmax - cg) < 64 ? (cmax - cg) : 64;
+        __syncwarp();
+        float v[64];
+        tmem_ld32(tacc + (uint32_t)cg, *reinterpret_cast<float(*)[32]>(&v[0]));
+        if (ncol > 32) tmem_ld32(tacc + (uint32_t)(cg + 32), *reinterpret_cast<float(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (cg + 64 >= cmax) {                    // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int jj = 0; jj < 64; ++jj)
+            if (jj < ncol) v[jj] += __ldg(p.bias + co0 + cg + jj);
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h * 32 < ncol) {                  // uniform across the epilogue group
+              float s1[32], s2[32];
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) { s1[jj] = v[h * 32 + jj]; s2[jj] = s1[jj] * s1[jj]; }
+              float cs = warp_transpose_reduce32(s1, lane);
+              float css = warp_transpose_reduce32(s2, lane);
+              red[(q * 2 + 0) * 32 + lane] = cs;
+              red[(q * 2 + 1) * 32 + lane] = css;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (etid < 32 && h * 32 + etid < ncol) {
+                float a = red[0 * 32 + etid] + red[2 * 32 + etid] + red[4 * 32 + etid] + red[6 * 32 + etid];
+                float b = red[1 * 32 + etid] + red[3 * 32 + etid] + red[5 * 32 + etid] + red[7 * 32 + etid];
+                double* st = p.stats + ((size_t)n_img * d.Co_total + d.co_off + co0 + cg + h * 32 + etid) * 2;
+                atomicAdd(st, (double)a);
+                atomicAdd(st + 1, (double)b);
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+          }
+        }
+        if (nchw) {
+          float* y = reinterpret_cast<float*>(p.y);
+          const int plane = d.Ho * d.Wo;
+          const int n = opix / plane, pp = opix - n * plane;
+#pragma unroll
+          for (int jj = 0; jj < 64; ++jj)
+            if (jj < ncol)
+              y[((size_t)n * d.Co_total + d.co_off + co0 + cg + jj) * plane + pp] = apply_act(v[jj], d.act);
+        } else if (p.tstore && vec && !accum && ncol == 64) {
+          // ---- TMA store of a [128 rows x 64 cols] group through a 128B-swizzled staging buffer
+          const uint32_t sb = sgrp & 1;
+          if (etid == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint8_t* dstrow = stage_gen + sb * (BM * 128) + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+            *reinterpret_cast<uint4*>(dstrow + ((g ^ (row & 7)) << 4)) = pack8(o);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0) {
+            tma_store_2d(&mapC, sStage + sb * (BM * 128), d.co_off + co0 + cg, opix0);
+            tma_pending = true;
+          }
+          ++sgrp;
+        } else if (vec && (ncol == 64 || ncol == 32 || ncol == 16)) {
+          // ---- manual flush: per-warp skewed staging, then 16-byte chunks, consecutive lanes along a row
+          if (p.tstore) {                         // the TMA buffers alias this region: drain them first
+            if (etid == 0 && tma_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); tma_pending = false; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 8 < ncol) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+              *reinterpret_cast<uint4*>(stage_w + lane * STAGE_PITCH + g * 16) = pack8(o);
+            }
+          }
+          __syncwarp();
+          const int lg = ncol == 64 ? 3 : (ncol == 32 ? 2 : 1);       // log2(chunks per row)
+          __nv_bfloat16* ybase = reinterpret_cast<__nv_bfloat16*>(p.y) + d.co_off + co0 + cg;
+#pragma unroll
+          for (int itn = 0; itn < 8; ++itn) {
+            const int idx = itn * 32 + lane;
+            if (idx < (32 << lg)) {               // uniform per warp
+              const int r = idx >> lg, ch = idx & ((1 << lg) - 1);
+              uint4 val = *reinterpret_cast<const uint4*>(stage_w + r * STAGE_PITCH + ch * 16);
+              const int op = __shfl_sync(0xffffffffu, opix, r);
+              __nv_bfloat16* dst = ybase + (size_t)op * d.Co_total + ch * 8;
+              if (accum) {
+                float a[8], b[8];
+                unpack8(val, a);
+                unpack8(*reinterpret_cast<const uint4*>(dst), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += b[e];
+                val = pack8(a);
+              }
+              *reinterpret_cast<uint4*>(dst) = val;
+            }
+          }
+          __syncwarp();
+        } else {
+          __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)opix * d.Co_total + d.co_off + co0 + cg;
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (e < ncol) {
+              float val = apply_act(v[e], d.act);
+              if (accum) val += __bfloat162float(y[e]);
+              y[e] = __float2bfloat16_rn(val);
+            }
+        }
+      }
+    }
+    if (etid == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct Tiling { int Wt, R; };
+bool pick_tiling(const msg_conv_desc* d, Tiling* t) {
+  if (d->Wg >= 128) {
+    if (d->Wg % 128) return false;
+    t->Wt = 128; t->R = 1;
+    return true;
+  }
+  if (128 % d->Wg) return false;
+  t->Wt = d->Wg; t->R = 128 / d->Wg;
+  return d->Hg % t->R == 0;
+}
+int pick_bn(int Cout) {
+  int tiles = (Cout + 255) / 256;
+  int per = (Cout + tiles - 1) / tiles;
+  int bn = (per + 15) / 16 * 16;
+  if (bn > 64 && bn % 64 && (bn + 63) / 64 * 64 <= 256) bn = (bn + 63) / 64 * 64;   // whole 64-column store groups
+  return bn < 16 ? 16 : bn;
+}
+
+}  // namespace
+
+bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y) {
+  if (d->dtype != MSG_BF16) return false;
+  if (d->flags & MSG_CONV_IN_NORM) return false;
+  if (d->Cin % 64 || (d->Ci_total & 7) || (d->ci_off & 7)) return false;
+  if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
+  if (!(d->flags & MSG_CONV_OUT_NCHW_F32) && ((uintptr_t)y & 15)) return false;
+  if (d->in_stride != 1 && d->in_stride != 2) return false;
+  Tiling t;
+  if (!pick_tiling(d, &t)) return false;
+  if (t.Wt * d->in_stride > 256 || t.R * d->in_stride > 256) return false;
+  if ((long long)d->N * d->Hg * d->Wg / BM > 0x7fffffffLL / 8) return false;
+  return get_encode() != nullptr;
+}
+
+int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+               double* stats, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled unavailable");
+  Tiling tl;
+  MSG_REQUIRE(pick_tiling(d, &tl), MSG_ERR_UNSUPPORTED, "conv_tma: unsupported plane geometry");
+  TmaParams p;
+  p.d = *d; p.bias = bias; p.y = y; p.stats = stats;
+  p.BN = pick_bn(d->Cout);
+  p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
+  p.m_tiles = (int)((long long)d->N * d->Hg * d->Wg / BM);
+  p.Wt = tl.Wt; p.R = tl.R;
+  p.cblocks = d->Cin / 64;
+  p.nkb = d->KH * d->KW * p.cblocks;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
+  const int K = d->KH * d->KW * d->Cin;
+  const int stage_bytes = A_BYTES + p.BN * BK * 2;
+  const int fixed = STAGE_BYTES + 1024 + 8 * 16 + 64 + 1024;
+  p.tstore = (!(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
+              d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&
+              (((uintptr_t)y) & 15) == 0) ? 1 : 0;
+  int stages = (220 * 1024 - fixed) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+
+  CUtensorMap mapA, mapB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->Wi * d->Ci_total * 2,
+                             (cuuint64_t)d->Hi * d->Wi * d->Ci_total * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(tl.Wt * d->in_stride), (cuuint32_t)(tl.R * d->in_stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->in_stride, (cuuint32_t)d->in_stride, 1};
+    void* base = (void*)((const __nv_bfloat16*)x + d->ci_off);
+    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  CUtensorMap mapC = mapB;   // unused unless tstore
+  if (p.tstore) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->Co_total, (cuuint64_t)d->N * d->Ho * d->Wo};
+    cuuint64_t strides[1] = {(cuuint64_t)d->Co_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mapC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled(C) failed with %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  const int total = p.m_tiles * p.n_tiles;
+  if (grid > total) grid = total;
+  conv_tma_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p);
+  return check_launch("conv_tma_kernel");
+}
+
+}  // namespace msg

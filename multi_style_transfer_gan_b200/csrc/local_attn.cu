@@ -222,6 +222,11 @@ local_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, int
 }  // namespace
 }  // namespace msg
 
+namespace msg {
+bool local_attn_tc_supported(int dtype, int C, const void* qkv, const void* out);
+int local_attn_fwd_tc(const void* qkv, int N, int H, int W, int C, void* out, cudaStream_t st);
+}  // namespace msg
+
 using namespace msg;
 
 static unsigned la_grid(long long nwin) {
@@ -234,10 +239,11 @@ extern "C" int msg_local_attn_fwd(int dtype, const void* qkv, int N, int H, int 
   MSG_REQUIRE(ws == 4, MSG_ERR_UNSUPPORTED, "local_attn: only window_size=4 (enhanced_generator.py:102)");
   MSG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, MSG_ERR_SHAPE,
               "local_attn: H, W must be multiples of the window size (got %dx%d)", H, W);
+  cudaStream_t st = as_stream(stream);
+  if (local_attn_tc_supported(dtype, C, qkv, out)) return local_attn_fwd_tc(qkv, N, H, W, C, out, st);
   size_t smem = (size_t)(4 * P * C + 2 * P) * sizeof(float) + 2 * P * sizeof(int);
   MSG_REQUIRE(smem <= 227 * 1024, MSG_ERR_UNSUPPORTED, "local_attn: C=%d too large", C);
   long long nwin = (long long)N * (H / 4) * (W / 4);
-  cudaStream_t st = as_stream(stream);
   if (dtype == MSG_F32) {
     cudaFuncSetAttribute(local_attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     local_attn_fwd_kernel<float><<<la_grid(nwin), LA_TPB, smem, st>>>((const float*)qkv, N, H, W, C, (float*)out);

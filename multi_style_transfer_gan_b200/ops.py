@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, CONV_ACCUM, CONV_FORCE_SIMT, CONV_IN_NORM,
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, CONV_ACCUM, CONV_FORCE_GATHER, CONV_FORCE_SIMT, CONV_IN_NORM,
                    CONV_OUT_NCHW_F32, CONV_STATS, PACK_CONVT_PHASES, PACK_DGRAD_S1, PACK_FWD, ConvDesc)
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}

@@ -33,6 +33,9 @@ LAYERS = [
     ("convT", 128, 64, 4, 2, 1, 1, 32, 32),   # up2.0
     ("conv", 64, 8, 7, 1, 3, 1, 64, 64),      # output (padded filters)
     ("conv", 64, 128, 4, 2, 1, 1, 48, 80),    # plane not a multiple of 128 -> partial tiles
+    ("conv", 64, 64, 3, 1, 1, 1, 16, 256),    # Wg = 256: two 128-pixel tiles per row
+    ("conv", 64, 320, 1, 1, 0, 1, 32, 32),    # Cout > 256: two N tiles of 160
+    ("conv", 128, 64, 4, 2, 1, 1, 32, 512),   # stride 2 with Wg = 256
 ]
 
 
@@ -54,12 +57,16 @@ def test_tc_vs_simt_and_torch(case):
     use_stats = (H * W if kind == "convT" else Ho * Wo) % 128 == 0
     st_tc = ops.new_stats(N, Cout, DEV) if use_stats else None
     st_si = ops.new_stats(N, Cout, DEV) if use_stats else None
-    y_tc = g.forward(xh, wp, b, stats=st_tc)
+    y_tc = g.forward(xh, wp, b, stats=st_tc)                    # TMA kernel when the geometry allows, else gather
     y_si = g.forward(xh, wp, b, stats=st_si, extra_flags=ops.CONV_FORCE_SIMT)
+    st_ga = ops.new_stats(N, Cout, DEV) if use_stats else None
+    y_ga = g.forward(xh, wp, b, stats=st_ga, extra_flags=ops.CONV_FORCE_GATHER)   # cp.async gather kernel
     assert_parity(nchw(y_tc), ref, 1e-2, "tc vs torch")
     assert_parity(nchw(y_tc), nchw(y_si), 1e-2, "tc vs simt")
+    assert_parity(nchw(y_ga), nchw(y_si), 1e-2, "gather vs simt")
     if use_stats:
         assert_parity(st_tc, st_si, 1e-4, "stats tc vs simt")
+        assert_parity(st_ga, st_si, 1e-4, "stats gather vs simt")
     # fused activation epilogues
     y_act = g.forward(xh, wp, b, act=ops.ACT_LRELU)
     assert_parity(nchw(y_act), F.leaky_relu(ref, 0.2), 1e-2, "lrelu epilogue")
