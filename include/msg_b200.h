@@ -93,6 +93,40 @@ typedef struct {
 int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                double* stats, const double* in_stats, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * "Row-slab" convolution (bf16, W % 8 == 0): stride-1, same-size convs with small N, several taps
+ * sharing one input row slab -- the 7x7 convs (enhanced_generator.py:92,137) and the fused
+ * MultiScaleBlock branches (:52-71, one launch writes the concatenated tensor).  A k-block is an
+ * (input row offset dy, 64-channel block cb) pair; each of its taps has a horizontal shift sx, its
+ * own [ncols x 64] weight tile (row tp*ncols of w_slab) and an accumulator column offset.
+ *   acc[x][tap_acc_col[tp] + c] (+)= sum_k x[n, y + kb_dy, x + tap_sx[tp], cb*64 + k] * w_slab[tp*ncols + c][k]
+ * pixel_pair_k (3-channel image padded to 8 channels): K=16 of one MMA = this pixel and the next;
+ * all taps of a k-block share w_slab tile kb, tap_kstep selects the 16-wide K slice.
+ * ------------------------------------------------------------------------------------------- */
+#define MSG_SLAB_MAX_KBLOCKS 32
+#define MSG_SLAB_MAX_TAPS 128
+typedef struct {
+  int dtype;
+  int N, H, W, Ci_total, ci_off, Cin;
+  int Co_total, co_off;
+  int Ntot;        /* accumulator columns (multiple of 16, <= 256)                                */
+  int n_store;     /* leading columns actually written to y (<= Ntot)                             */
+  int ncols;       /* columns per tap (multiple of 16)                                            */
+  int halo;        /* max |tap_sx|                                                                */
+  int pixel_pair_k;
+  int act;
+  unsigned flags;  /* MSG_CONV_STATS | MSG_CONV_OUT_NCHW_F32                                      */
+  int n_kblocks, n_taps;
+  int kb_dy[MSG_SLAB_MAX_KBLOCKS], kb_cb[MSG_SLAB_MAX_KBLOCKS], kb_tap_begin[MSG_SLAB_MAX_KBLOCKS + 1];
+  int tap_sx[MSG_SLAB_MAX_TAPS], tap_acc_col[MSG_SLAB_MAX_TAPS], tap_first[MSG_SLAB_MAX_TAPS],
+      tap_kstep[MSG_SLAB_MAX_TAPS];
+} msg_slab_desc;
+/* x [N,H,W,Ci_total] bf16; w_slab bf16 [n_tiles*ncols][64]; bias fp32 [Ntot] or NULL (program column
+ * order); y [N,H,W,Co_total] bf16 (or fp32 NCHW [N,Co_total,H,W] with MSG_CONV_OUT_NCHW_F32);
+ * stats fp64 [N][Co_total][2] accumulated (MSG_CONV_STATS). */
+int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* w_slab, const float* bias, void* y,
+                  double* stats, void* stream);
+
 /* wgrad of the same descriptor: dw[co][th][tw][ci] (fp32, packed layout, ACCUMULATED into) =
  * sum over pixels of dy[..., co] * gathered x[..., ci].  Replaces autograd's conv weight grads for
  * every conv above (enhanced_train.py:84,121). */

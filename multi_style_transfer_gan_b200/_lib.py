@@ -26,6 +26,20 @@ class ConvDesc(ctypes.Structure):
         "out_off_h", "out_off_w", "act")] + [("flags", c_uint), ("in_act", c_int)]
 
 
+SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS = 32, 128
+
+
+class SlabDesc(ctypes.Structure):
+    """mirrors msg_slab_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in (
+        "dtype", "N", "H", "W", "Ci_total", "ci_off", "Cin", "Co_total", "co_off", "Ntot", "n_store", "ncols",
+        "halo", "pixel_pair_k", "act")] + [("flags", c_uint), ("n_kblocks", c_int), ("n_taps", c_int),
+        ("kb_dy", c_int * SLAB_MAX_KBLOCKS), ("kb_cb", c_int * SLAB_MAX_KBLOCKS),
+        ("kb_tap_begin", c_int * (SLAB_MAX_KBLOCKS + 1)),
+        ("tap_sx", c_int * SLAB_MAX_TAPS), ("tap_acc_col", c_int * SLAB_MAX_TAPS),
+        ("tap_first", c_int * SLAB_MAX_TAPS), ("tap_kstep", c_int * SLAB_MAX_TAPS)]
+
+
 _P = c_void_p
 # name -> argtypes (everything returns int except msg_last_error)
 SIGNATURES = {
@@ -34,6 +48,7 @@ SIGNATURES = {
     "msg_sm_count": [],
     "msg_conv2d": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "msg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
+    "msg_conv_slab": [ctypes.POINTER(SlabDesc), _P, _P, _P, _P, _P, _P],
     "msg_pack_conv_weight": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_unpack_conv_wgrad": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "msg_bias_grad": [c_int, _P, c_ll, c_int, c_int, c_int, _P, _P],

@@ -1,0 +1,126 @@
+"""Host-side "programs" for the row-slab convolution kernel (csrc/conv_slab.cu): which input-row slabs
+a tile needs, which taps reuse each slab, and how the master weights are laid out as [ncols x 64]
+tiles.  Three users (all stride-1, same-size, bf16):
+  * the fused MultiScaleBlock branches (enhanced_generator.py:52-71): 1x1 + 3x3 dil 1/2/4 in ONE launch
+    writing the concatenated [N,H,W,C] tensor (+ the shared InstanceNorm statistics);
+  * the 7x7 output conv + tanh (:137-138), N = 3 padded to 16;
+  * the 7x7 input conv (:92) on the 3-channel image padded to 8 channels ("pixel-pair K").
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from ._lib import SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS, SlabDesc
+
+
+class SlabProgram:
+    def __init__(self, Cin, Ntot, n_store, ncols, halo, pixel_pair, kblocks):
+        """kblocks: list of (dy, cb, [(sx, acc_col, kstep, weight_key), ...])"""
+        self.Cin, self.Ntot, self.n_store, self.ncols, self.halo, self.pixel_pair = Cin, Ntot, n_store, ncols, halo, pixel_pair
+        self.kblocks = kblocks
+        taps = [t for _, _, ts in kblocks for t in ts]
+        if len(kblocks) > SLAB_MAX_KBLOCKS or len(taps) > SLAB_MAX_TAPS:
+            raise ValueError("slab program too large")
+        self.n_taps = len(taps)
+
+    def fill(self, d):
+        d.Cin, d.Ntot, d.n_store, d.ncols, d.halo, d.pixel_pair_k = (self.Cin, self.Ntot, self.n_store, self.ncols,
+                                                                      self.halo, int(self.pixel_pair))
+        d.n_kblocks, d.n_taps = len(self.kblocks), self.n_taps
+        seen, tp = set(), 0
+        for kb, (dy, cb, taps) in enumerate(self.kblocks):
+            d.kb_dy[kb], d.kb_cb[kb], d.kb_tap_begin[kb] = dy, cb, tp
+            for sx, acc_col, kstep, _ in taps:
+                d.tap_sx[tp], d.tap_acc_col[tp], d.tap_kstep[tp] = sx, acc_col, kstep
+                d.tap_first[tp] = int(acc_col not in seen)
+                seen.add(acc_col)
+                tp += 1
+        d.kb_tap_begin[len(self.kblocks)] = tp
+
+
+def msb_program(C):
+    """All four MultiScaleBlock branches; branch b writes accumulator columns [(b-1)C/4, bC/4)."""
+    q = C // 4
+    branches = [(1, 1), (3, 1), (3, 2), (3, 4)]   # (k, dilation) of branch1..4
+    kblocks = []
+    for dy in (-4, -2, -1, 0, 1, 2, 4):
+        for cb in range(C // 64):
+            taps = []
+            for b, (k, dil) in enumerate(branches):
+                for kh in range(k):
+                    if (kh - k // 2) * dil != dy:
+                        continue
+                    for kw in range(k):
+                        taps.append(((kw - k // 2) * dil, b * q, 0, (b, kh, kw, cb)))
+            kblocks.append((dy, cb, taps))
+    return SlabProgram(C, C, C, q, 4, False, kblocks)
+
+
+def msb_weight_slab(prog, weights, dtype=torch.bfloat16):
+    """weights: [w_branch1 [q,C,1,1], w_branch2..4 [q,C,3,3]] fp32 -> bf16 [n_taps*q, 64]."""
+    rows = []
+    for _, _, taps in prog.kblocks:
+        for _, _, _, (b, kh, kw, cb) in taps:
+            rows.append(weights[b][:, cb * 64:(cb + 1) * 64, kh, kw])
+    return torch.cat(rows, 0).to(dtype).contiguous()
+
+
+def conv7_out_program(c):
+    kblocks = []
+    for kh in range(7):
+        for cb in range(c // 64):
+            kblocks.append((kh - 3, cb, [(kw - 3, 0, 0, (kh, kw, cb)) for kw in range(7)]))
+    return SlabProgram(c, 16, 3, 16, 3, False, kblocks)
+
+
+def conv7_out_weight_slab(prog, w, dtype=torch.bfloat16):
+    """w: [3, c, 7, 7] fp32 -> bf16 [n_taps*16, 64] (filters 3..15 zero)."""
+    rows = []
+    for _, _, taps in prog.kblocks:
+        for _, _, _, (kh, kw, cb) in taps:
+            t = torch.zeros(16, 64, device=w.device, dtype=torch.float32)
+            t[:3] = w[:, cb * 64:(cb + 1) * 64, kh, kw]
+            rows.append(t)
+    return torch.cat(rows, 0).to(dtype).contiguous()
+
+
+def conv7_in_program(c):
+    """7x7 conv on the image padded to 8 channels: one MMA (K=16) covers taps kw = 2j, 2j+1."""
+    kblocks = [(kh - 3, 0, [(2 * j - 3, 0, j, (kh, j)) for j in range(4)]) for kh in range(7)]
+    return SlabProgram(8, c, c, c, 3, True, kblocks)
+
+
+def conv7_in_weight_slab(prog, w, dtype=torch.bfloat16):
+    """w: [c, 3, 7, 7] fp32 -> bf16 [7*c, 64]; row (kh, co), k = j*16 + p*8 + ch  <->  w[co, ch, kh, 2j+p]."""
+    c = w.shape[0]
+    t = torch.zeros(7, c, 4, 2, 8, device=w.device, dtype=torch.float32)
+    wp = torch.zeros(c, 8, 7, 8, device=w.device, dtype=torch.float32)
+    wp[:, :3, :, :7] = w
+    # wp[co, ch, kh, kw] -> t[kh, co, j, p, ch] with kw = 2j + p
+    t.copy_(wp.reshape(c, 8, 7, 4, 2).permute(2, 0, 3, 4, 1))
+    return t.reshape(7 * c, 64).to(dtype).contiguous()
+
+
+def conv_slab(prog, x, w_slab, bias, out=None, co_off=0, stats=None, act=ops.ACT_NONE, nchw_out=None, ci_off=0):
+    """x: [N,H,W,Ci_total] bf16.  Writes columns [co_off, co_off+n_store) of `out` [N,H,W,Co_total] bf16, or the
+    fp32 NCHW tensor `nchw_out` [N,n_store,H,W]."""
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    d = SlabDesc()
+    d.dtype, d.N, d.H, d.W, d.Ci_total, d.ci_off = _lib.BF16, N, H, W, Ci_total, ci_off
+    prog.fill(d)
+    flags = 0
+    if stats is not None:
+        flags |= _lib.CONV_STATS
+    if nchw_out is not None:
+        flags |= _lib.CONV_OUT_NCHW_F32
+        y, d.Co_total = nchw_out, prog.n_store
+    else:
+        if out is None:
+            out = torch.empty((N, H, W, prog.n_store), device=x.device, dtype=x.dtype)
+        y, d.Co_total = out, out.shape[3]
+    d.co_off, d.act, d.flags = co_off, act, flags
+    _lib.call("msg_conv_slab", ctypes.byref(d), ops._p(x), ops._p(w_slab), ops._p(bias), ops._p(y), ops._p(stats),
+              ops._stream())
+    return nchw_out if nchw_out is not None else out

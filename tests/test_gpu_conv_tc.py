@@ -92,3 +92,57 @@ def test_tc_nchw_tanh_epilogue_and_accumulate():
     out = nhwc(base.float())
     g2.forward(nhwc(x), g2.pack_fwd(w2, dt), None, out=out, extra_flags=ops.CONV_ACCUM)
     assert_parity(nchw(out), base.float() + F.conv2d(x, w2, None, padding=1), 1e-2, "accumulate")
+
+
+# ---- row-slab kernel (csrc/conv_slab.cu) ---------------------------------------------------------
+@pytest.mark.parametrize("C,H,W", [(64, 16, 128), (64, 8, 256), (128, 8, 128), (64, 12, 72), (256, 4, 128)])
+def test_slab_msb_branches(C, H, W):
+    """fused 1x1 + 3x3 dil 1/2/4 branches == the four separate convs + cat, incl. shared IN statistics"""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(0)
+    N, q, dt = 2, C // 4, torch.bfloat16
+    x = torch.randn(N, C, H, W, device=DEV).to(dt).float()
+    ws = [(torch.randn(q, C, k, k, device=DEV) * (1.0 / (C * k * k) ** 0.5)).to(dt).float() for k in (1, 3, 3, 3)]
+    bs = [torch.randn(q, device=DEV) for _ in range(4)]
+    ref = torch.cat([F.conv2d(x, w, b, padding=(w.shape[2] // 2) * d, dilation=d)
+                     for w, b, d in zip(ws, bs, (1, 1, 2, 4))], 1)
+    prog = slab.msb_program(C)
+    wsl = slab.msb_weight_slab(prog, ws)
+    st = ops.new_stats(N, C, DEV)
+    y = slab.conv_slab(prog, nhwc(x), wsl, torch.cat(bs).contiguous(), stats=st)
+    assert_parity(nchw(y), ref, 1e-2, "fused branches")
+    st_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1)
+    assert_parity(st, st_ref, 3e-3, "stats")
+
+
+@pytest.mark.parametrize("c,H,W", [(64, 16, 128), (64, 8, 384), (128, 8, 128), (64, 24, 40)])
+def test_slab_output_conv(c, H, W):
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(1)
+    N, dt = 2, torch.bfloat16
+    x = torch.randn(N, c, H, W, device=DEV).to(dt).float()
+    w = (torch.randn(3, c, 7, 7, device=DEV) * 0.02).to(dt).float()
+    b = torch.randn(3, device=DEV)
+    prog = slab.conv7_out_program(c)
+    y = torch.empty(N, 3, H, W, device=DEV)
+    bias16 = torch.zeros(16, device=DEV)
+    bias16[:3] = b
+    slab.conv_slab(prog, nhwc(x), slab.conv7_out_weight_slab(prog, w), bias16, act=ops.ACT_TANH, nchw_out=y)
+    assert_parity(y, torch.tanh(F.conv2d(x, w, b, padding=3)), 1e-2, "7x7 output conv + tanh")
+
+
+@pytest.mark.parametrize("c,H,W", [(64, 16, 128), (64, 8, 256), (16, 8, 128), (64, 20, 56)])
+def test_slab_input_conv(c, H, W):
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(2)
+    N, dt = 2, torch.bfloat16
+    x = (torch.rand(N, 3, H, W, device=DEV) * 2 - 1).to(dt).float()
+    w = (torch.randn(c, 3, 7, 7, device=DEV) * 0.1).to(dt).float()
+    b = torch.randn(c, device=DEV)
+    prog = slab.conv7_in_program(c)
+    x8 = ops.nchw_to_nhwc(x, dt, 8)
+    st = ops.new_stats(N, c, DEV)
+    y = slab.conv_slab(prog, x8, slab.conv7_in_weight_slab(prog, w), b, stats=st)
+    ref = F.conv2d(x, w, b, padding=3)
+    assert_parity(nchw(y), ref, 1e-2, "7x7 input conv")
+    assert_parity(st, torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1), 3e-3, "stats")
