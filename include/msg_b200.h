@@ -114,6 +114,9 @@ typedef struct {
   int ncols;       /* columns per tap (multiple of 16)                                            */
   int halo;        /* max |tap_sx|                                                                */
   int pixel_pair_k;
+  int n_chains;    /* 1, 2 or 4 independent accumulation chains (TMEM column groups Ntot apart, summed
+                      in the epilogue): back-to-back tcgen05.mma into the SAME columns are latency-bound
+                      when N is small; n_chains * Ntot <= 256                                       */
   int act;
   unsigned flags;  /* MSG_CONV_STATS | MSG_CONV_OUT_NCHW_F32                                      */
   int n_kblocks, n_taps;

@@ -17,6 +17,7 @@
 // Pipeline = conv_tma.cu's: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue, smem ring of
 // slabs, double-buffered TMEM accumulators, persistent CTAs (one per SM).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -56,6 +57,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,9 +128,15 @@ struct SlabParams {
   int stages, tmem_cols;
   int Ws;             // slab width in pixels (128 + 2*halo, padded to a multiple of 8)
   int a_bytes;        // bytes of one A slab (chunks * Ws * 16)
-  int b_bytes;        // bytes of one B stage (max taps per k-block * ncols * 128)
+  int b_bytes;        // bytes of one B stage (0 when the weights are resident)
+  int b_resident;     // all weight tiles stay in smem for the whole kernel (loaded once): total bytes, or 0
+  int b_box_taps;     // streaming mode: weight tiles fetched per TMA box
   int chunks;         // K chunks per slab (8, or 1 in pixel-pair mode)
   int segs;           // 128-pixel segments per image row
+  int a_mode;         // 0: chunk planes [chunk][pixel][16 B], no swizzle (8 TMA boxes per slab)
+                      // 1: pixel rows [pixel][128 B], 128B swizzle, ONE TMA box; tap shift = +128 B/pixel on the
+                      //    descriptor start, swizzle phase carried by the descriptor's base_offset field
+                      // 2: as 1 with base_offset = 0
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -136,14 +148,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int S = p.stages;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sB = base;                                   // B stages first: 1024-byte aligned sub-tiles
-  const uint32_t sA = sB + S * p.b_bytes;
+  const uint32_t sB = base;                                   // weight tiles first: 1024-byte aligned
+  const uint32_t sA = sB + (p.b_resident ? p.b_resident : S * p.b_bytes);
   const uint32_t sStage = (sA + S * p.a_bytes + 127u) & ~127u;
-  const uint32_t sRed = sStage + 4 * 32 * STAGE_PITCH;
-  const uint32_t sBar = sRed + 1024;
+  const uint32_t sRed = sStage + 4 * 32 * STAGE_PITCH;        // per-warp column sums [4][2][256] floats
+  const uint32_t sBar = sRed + 8192;
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
+  const uint32_t wres_bar = sBar + 8u * (2 * S + 4);          // "resident weights have landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
   auto tfull_bar = [&](int b) { return sBar + 8u * (2 * S + b); };
@@ -153,6 +166,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+      mbar_init(wres_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -167,13 +181,21 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = d.N * d.H * p.segs;
+  const int t_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);   // contiguous range per CTA
+  const int t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
   const int tap_bytes = d.ncols * 128;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      if (p.b_resident) {       // all weight tiles, once: they stay in smem for every tile of this CTA
+        const int tiles_total = d.pixel_pair_k ? d.n_kblocks : d.n_taps;
+        mbar_expect_tx(wres_bar, (uint32_t)(((tiles_total + p.b_box_taps - 1) / p.b_box_taps) * p.b_box_taps * tap_bytes));
+        for (int bx = 0; bx * p.b_box_taps < tiles_total; ++bx)
+          tma_load_2d(sB + bx * p.b_box_taps * tap_bytes, &mapB, wres_bar, 0, bx * p.b_box_taps * d.ncols);
+      }
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int seg = t % p.segs, ny = t / p.segs;
         const int yrow = ny % d.H, img = ny / d.H;
         const int x0 = seg * BM - d.halo;
@@ -181,55 +203,92 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int s = it % S;
           if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
           const int t0 = d.kb_tap_begin[kb], t1 = d.kb_tap_begin[kb + 1];
-          const int nb = d.pixel_pair_k ? 1 : (t1 - t0);
-          mbar_expect_tx(full_bar(s), p.a_bytes + nb * tap_bytes);
-          // slab = `chunks` planes of [Ws pixels][16 B]: one box {8 ch, Ws, 1, 1} per 8-channel chunk
-          for (int ch = 0; ch < p.chunks; ++ch)
-            tma_load_4d(sA + s * p.a_bytes + ch * (p.Ws * 16), &mapA, full_bar(s), d.kb_cb[kb] * 64 + ch * 8, x0,
-                        yrow + d.kb_dy[kb], img);
-          if (d.pixel_pair_k) {
-            tma_load_2d(sB + s * p.b_bytes, &mapB, full_bar(s), 0, kb * d.ncols);
+          const int nbox = p.b_resident ? 0 : (d.pixel_pair_k ? 1 : (t1 - t0 + p.b_box_taps - 1) / p.b_box_taps);
+          mbar_expect_tx(full_bar(s), p.a_bytes + nbox * p.b_box_taps * tap_bytes);
+          if (p.a_mode != 0) {
+            // slab = [Ws pixels][64 channels], 128B-swizzled: one box {64 ch, Ws, 1, 1}
+            tma_load_4d(sA + s * p.a_bytes, &mapA, full_bar(s), d.kb_cb[kb] * 64, x0, yrow + d.kb_dy[kb], img);
           } else {
-            for (int tp = t0; tp < t1; ++tp)
-              tma_load_2d(sB + s * p.b_bytes + (tp - t0) * tap_bytes, &mapB, full_bar(s), 0, tp * d.ncols);
+            // slab = `chunks` planes of [Ws pixels][16 B]: one box {8 ch, Ws, 1, 1} per 8-channel chunk
+            for (int ch = 0; ch < p.chunks; ++ch)
+              tma_load_4d(sA + s * p.a_bytes + ch * (p.Ws * 16), &mapA, full_bar(s), d.kb_cb[kb] * 64 + ch * 8, x0,
+                          yrow + d.kb_dy[kb], img);
           }
+          // streamed weights: boxes of b_box_taps tiles (small TMA requests are latency-bound, so few big ones)
+          const int row0 = (d.pixel_pair_k ? kb : t0) * d.ncols;
+          for (int bx = 0; bx < nbox; ++bx)
+            tma_load_2d(sB + s * p.b_bytes + bx * p.b_box_taps * tap_bytes, &mapB, full_bar(s), 0,
+                        row0 + bx * p.b_box_taps * d.ncols);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.ncols >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t lbo = d.pixel_pair_k ? 16u : (uint32_t)(p.Ws * 16);
-      const int ksteps = d.pixel_pair_k ? 1 : 4;              // UMMA_K=16 steps per tap
-      uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+    // The WHOLE warp runs this loop (warp-uniform control flow, per-tap constants read from the kernel
+    // parameters = constant bank) so that descriptors stay in uniform registers; only the tcgen05
+    // instructions themselves are issued by one elected lane.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.ncols >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t lbo = (uint32_t)(p.Ws * 16);
+    const uint64_t sw128_hi = make_sw128_desc(0);             // descriptor with a zero start address
+    const int nch = d.n_chains;
+    const uint32_t ch1 = nch > 1 ? (uint32_t)d.Ntot : 0u;
+    const uint32_t ch2 = nch > 2 ? (uint32_t)(2 * d.Ntot) : 0u;
+    const uint32_t ch3 = nch > 2 ? (uint32_t)(3 * d.Ntot) : ch1;
+    uint32_t it = 0, lt = 0;
+    if (p.b_resident) mbar_wait(wres_bar, 0);
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
+      const int buf = lt & 1;
+      if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains);
+      for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot);
-        for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(full_bar(s), (it / S) & 1);
-          tc_fence_after();
-          const uint32_t a0 = sA + s * p.a_bytes;
-          const uint32_t b0 = sB + s * p.b_bytes;
-          const int t0 = d.kb_tap_begin[kb], t1 = d.kb_tap_begin[kb + 1];
+        const uint32_t a0 = sA + s * p.a_bytes;
+        const uint32_t b0 = p.b_resident ? sB : sB + s * p.b_bytes;
+        const int t0 = d.kb_tap_begin[kb], t1 = d.kb_tap_begin[kb + 1];
+        if (p.a_mode != 0) {
+          // [pixel][128 B] slab, 128B swizzle: tap shift = +128 B per pixel on the start address; the
+          // swizzle is a function of the absolute smem address, so base_offset stays 0 (verified on B200)
           for (int tp = t0; tp < t1; ++tp) {
-            const uint32_t a_tap = a0 + (uint32_t)((d.halo + d.tap_sx[tp]) * 16);
-            const uint32_t b_tap = b0 + (d.pixel_pair_k ? 0u : (uint32_t)((tp - t0) * tap_bytes));
-            for (int ks = 0; ks < ksteps; ++ks) {
-              // 64-channel mode: K step ks = chunks 2ks, 2ks+1 (LBO apart); B advances 32 B in its 128 B row.
-              // pixel-pair mode: one K step = this pixel + the next one (LBO = 16 B); B row holds 4 taps' K.
-              const uint64_t da = make_noswz_desc(a_tap + (uint32_t)(ks * 2) * lbo, lbo);
-              const uint64_t db = make_sw128_desc(b_tap) + (uint64_t)((d.pixel_pair_k ? d.tap_kstep[tp] : ks) * 2);
-              umma_bf16(tacc + (uint32_t)d.tap_acc_col[tp], da, db, idesc, !(d.tap_first[tp] && ks == 0));
+            const uint64_t da = sw128_hi | (uint64_t)((a0 + (uint32_t)d.tap_sx[tp]) >> 4);     // tap_sx: byte offset (host)
+            const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);  // tap_kstep: byte offset
+            const uint32_t dcol = tacc + (uint32_t)d.tap_acc_col[tp];
+            const uint32_t first = (uint32_t)d.tap_first[tp];
+            if (elect_one()) {
+              umma_bf16(dcol, da, db, idesc, !first);
+              umma_bf16(dcol + ch1, da + 2, db + 2, idesc, !(first && nch > 1));
+              umma_bf16(dcol + ch2, da + 4, db + 4, idesc, !(first && nch > 2));
+              umma_bf16(dcol + ch3, da + 6, db + 6, idesc, !(first && nch > 2));
             }
           }
-          umma_commit(empty_bar(s));
+        } else if (d.pixel_pair_k) {
+          for (int tp = t0; tp < t1; ++tp) {
+            const uint64_t da = make_noswz_desc(a0 + (uint32_t)d.tap_sx[tp], 16u);
+            const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);
+            const int chain = (tp - t0) % nch;              // 4 pair-taps per row -> up to 4 chains
+            if (elect_one())
+              umma_bf16(tacc + (uint32_t)d.tap_acc_col[tp] + (uint32_t)(chain * d.Ntot), da, db, idesc, !(kb == 0 && (tp - t0) < nch));
+          }
+        } else {
+          for (int tp = t0; tp < t1; ++tp) {
+            const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);
+            const uint32_t dcol = tacc + (uint32_t)d.tap_acc_col[tp];
+            const uint32_t first = (uint32_t)d.tap_first[tp];
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(dcol, make_noswz_desc(a0 + (uint32_t)d.tap_sx[tp] + (uint32_t)(ks * 2) * lbo, lbo), db + (uint64_t)(ks * 2),
+                          idesc, !(first && ks == 0));
+            }
+          }
         }
-        umma_commit(tfull_bar(buf));
+        __syncwarp();
+        if (elect_one()) umma_commit(empty_bar(s));
       }
+      __syncwarp();
+      if (elect_one()) umma_commit(tfull_bar(buf));
     }
   } else {
     // ===================================== epilogue (warps 2-5) =====================================
@@ -238,20 +297,35 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
     uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);
-    const int etid = tid - 64;
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
+    float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
+    for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
+    __syncwarp();
+    int stat_img = -1;
+    auto flush_stats = [&]() {
+      if (stat_img >= 0) {
+        for (int c = lane; c < cmax; c += 32) {
+          double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
+          atomicAdd(st, (double)wsum[c]);
+          atomicAdd(st + 1, (double)wsum[256 + c]);
+          wsum[c] = 0.f; wsum[256 + c] = 0.f;
+        }
+      }
+      __syncwarp();
+    };
     const bool vec = !nchw && ((d.Co_total | d.co_off | cmax) & 7) == 0;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int seg = t % p.segs, ny = t / p.segs;
       const int yrow = ny % d.H, img = ny / d.H;
       const int buf = lt & 1;
       const int xcol = seg * BM + row;
       const bool valid = xcol < d.W;
       const int opix = (img * d.H + yrow) * d.W + (valid ? xcol : 0);
+      if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
       mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot) + ((uint32_t)(q * 32) << 16);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains) + ((uint32_t)(q * 32) << 16);
       for (int cg = 0; cg < cmax; cg += 64) {
         const int ncol = (cmax - cg) < 64 ? (cmax - cg) : 64;
         __syncwarp();
@@ -259,6 +333,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tmem_ld32(tacc + (uint32_t)cg, *reinterpret_cast<float(*)[32]>(&v[0]));
         if (ncol > 32) tmem_ld32(tacc + (uint32_t)(cg + 32), *reinterpret_cast<float(*)[32]>(&v[32]));
         tmem_ld_wait();
+        for (int c = 1; c < d.n_chains; ++c) {      // add the other accumulation chains
+          float u[64];
+          tmem_ld32(tacc + (uint32_t)(c * d.Ntot + cg), *reinterpret_cast<float(*)[32]>(&u[0]));
+          if (ncol > 32) tmem_ld32(tacc + (uint32_t)(c * d.Ntot + cg + 32), *reinterpret_cast<float(*)[32]>(&u[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 64; ++jj)
+            if (jj < 32 || ncol > 32) v[jj] += u[jj];
+        }
         if (cg + 64 >= cmax) {
           tc_fence_before();
           __syncwarp();
@@ -276,19 +359,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               float s1[32], s2[32];
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) { s1[jj] = valid ? v[h * 32 + jj] : 0.f; s2[jj] = s1[jj] * s1[jj]; }
-              float cs = warp_transpose_reduce32(s1, lane);
-              float css = warp_transpose_reduce32(s2, lane);
-              red[(q * 2 + 0) * 32 + lane] = cs;
-              red[(q * 2 + 1) * 32 + lane] = css;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (etid < 32 && h * 32 + etid < ncol) {
-                float a = red[0 * 32 + etid] + red[2 * 32 + etid] + red[4 * 32 + etid] + red[6 * 32 + etid];
-                float b = red[1 * 32 + etid] + red[3 * 32 + etid] + red[5 * 32 + etid] + red[7 * 32 + etid];
-                double* st = p.stats + ((size_t)img * d.Co_total + d.co_off + cg + h * 32 + etid) * 2;
-                atomicAdd(st, (double)a);
-                atomicAdd(st + 1, (double)b);
-              }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              const float cs = warp_transpose_reduce32(s1, lane);
+              const float css = warp_transpose_reduce32(s2, lane);
+              wsum[cg + h * 32 + lane] += cs;
+              wsum[256 + cg + h * 32 + lane] += css;
             }
           }
         }
@@ -335,6 +409,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       }
     }
+    if (do_stats) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -375,6 +450,8 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   MSG_REQUIRE(d->ncols >= 16 && d->ncols % 16 == 0 && d->ncols <= 256 && d->Ntot % 16 == 0 && d->Ntot <= 256 &&
                   d->n_store <= d->Ntot,
               MSG_ERR_SHAPE, "conv_slab: bad N configuration");
+  MSG_REQUIRE((d->n_chains == 1 || d->n_chains == 2 || d->n_chains == 4) && d->n_chains * d->Ntot <= 256, MSG_ERR_SHAPE,
+              "conv_slab: bad n_chains");
   MSG_REQUIRE(d->n_kblocks >= 1 && d->n_kblocks <= MSG_SLAB_MAX_KBLOCKS && d->n_taps >= 1 && d->n_taps <= MSG_SLAB_MAX_TAPS &&
                   d->halo >= 0 && d->halo <= 16,
               MSG_ERR_SHAPE, "conv_slab: program too large");
@@ -388,19 +465,43 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   p.chunks = d->pixel_pair_k ? 1 : 8;
   p.Ws = (BM + 2 * d->halo + (d->pixel_pair_k ? 1 : 0) + 7) / 8 * 8;
   MSG_REQUIRE(p.Ws <= 256, MSG_ERR_SHAPE, "conv_slab: halo too large");
-  p.a_bytes = p.chunks * p.Ws * 16;
+  static const int env_mode = [] { const char* e = getenv("MSG_SLAB_AMODE"); return e ? atoi(e) : 2; }();
+  p.a_mode = d->pixel_pair_k ? 0 : env_mode;
+  MSG_REQUIRE(p.a_mode != 0 || d->pixel_pair_k || d->n_chains == 1, MSG_ERR_UNSUPPORTED, "conv_slab: chunk-plane mode is single-chain");
+  p.a_bytes = p.a_mode != 0 ? p.Ws * 128 : p.chunks * p.Ws * 16;
   int max_taps = 0;
   for (int kb = 0; kb < d->n_kblocks; ++kb) {
     int nt = d->kb_tap_begin[kb + 1] - d->kb_tap_begin[kb];
     MSG_REQUIRE(nt >= 1, MSG_ERR_SHAPE, "conv_slab: empty k-block");
     if (nt > max_taps) max_taps = nt;
   }
-  p.b_bytes = (d->pixel_pair_k ? 1 : max_taps) * d->ncols * 128;
+  const int tap_bytes = d->ncols * 128;
+  int min_taps = max_taps;
+  for (int kb = 0; kb < d->n_kblocks; ++kb) {
+    int nt = d->kb_tap_begin[kb + 1] - d->kb_tap_begin[kb];
+    if (nt < min_taps) min_taps = nt;
+  }
+  const int n_tiles_total = d->pixel_pair_k ? d->n_kblocks : d->n_taps;
+  p.b_box_taps = d->pixel_pair_k ? 1 : min_taps;
+  while (p.b_box_taps * d->ncols > 256) --p.b_box_taps;                       // TMA box rows <= 256
+  static const bool env_res = [] { const char* e = getenv("MSG_SLAB_RESIDENT"); return !(e && e[0] == '0'); }();
+  const int res_bytes = ((n_tiles_total + p.b_box_taps - 1) / p.b_box_taps) * p.b_box_taps * tap_bytes;
+  p.b_resident = (env_res && res_bytes <= 104 * 1024) ? res_bytes : 0;
+  p.b_bytes = p.b_resident ? 0 : (d->pixel_pair_k ? 1 : (max_taps + p.b_box_taps - 1) / p.b_box_taps * p.b_box_taps) * tap_bytes;
   p.segs = (d->W + BM - 1) / BM;
+  // per-tap constants of the MMA issue loop, precomputed here and read from the constant bank:
+  //   tap_sx    <- byte offset of the tap's shifted view inside the A slab
+  //   tap_kstep <- byte offset of the tap's weight tile (or 16-wide K slice) inside the B stage / resident block
+  for (int kb = 0; kb < d->n_kblocks; ++kb)
+    for (int tp = d->kb_tap_begin[kb]; tp < d->kb_tap_begin[kb + 1]; ++tp) {
+      p.d.tap_sx[tp] = (d->halo + d->tap_sx[tp]) * (p.a_mode != 0 ? 128 : 16);
+      if (d->pixel_pair_k) p.d.tap_kstep[tp] = d->tap_kstep[tp] * 32 + (p.b_resident ? kb * tap_bytes : 0);
+      else p.d.tap_kstep[tp] = (p.b_resident ? tp : tp - d->kb_tap_begin[kb]) * tap_bytes;
+    }
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * d->Ntot) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 1024 + 8 * 16 + 64 + 1024;
+  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 256 + 1024 + p.b_resident;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_slab: stage of %d bytes does not fit twice in shared memory", stage_bytes);
@@ -412,18 +513,19 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->W * d->Ci_total * 2,
                              (cuuint64_t)d->H * d->W * d->Ci_total * 2};
-    cuuint32_t box[4] = {8, (cuuint32_t)p.Ws, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(p.a_mode != 0 ? 64 : 8), (cuuint32_t)p.Ws, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = (void*)((const __nv_bfloat16*)x + d->ci_off);
     CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, p.a_mode != 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_slab: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
     cuuint64_t dims[2] = {64, (cuuint64_t)(d->pixel_pair_k ? d->n_kblocks : d->n_taps) * d->ncols};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)d->ncols};
+    cuuint32_t box[2] = {64, (cuuint32_t)(d->ncols * p.b_box_taps)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_slab, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -22,6 +22,7 @@
 // (128 % Wg == 0 and Hg % (128/Wg) == 0).  Everything else takes the gather kernel (conv_tc.cu) or
 // the SIMT engine.  Same descriptor semantics as include/msg_b200.h.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -142,8 +143,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t sA = base;
   const uint32_t sB = sA + S * A_BYTES;
   const uint32_t sStage = sB + S * b_bytes;                 // epilogue staging, 1024-byte aligned
-  const uint32_t sRed = sStage + STAGE_BYTES;               // 8 x 32 floats
-  const uint32_t sBar = sRed + 1024;                        // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t sRed = sStage + STAGE_BYTES;               // per-warp column sums [4][2][256] floats
+  const uint32_t sBar = sRed + 8192;                        // full[S], empty[S], tfull[2], tempty[2]
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
@@ -170,6 +171,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // each CTA owns a CONTIGUOUS range of tiles (same image, neighbouring rows: L2 locality, and the
+  // epilogue can keep per-channel statistics on chip across its tiles)
+  const int t_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
   const int tiles_per_row = d.Wg / p.Wt;        // >= 1
   const int tile_rows = d.Hg / p.R;             // row groups per image
 
@@ -177,7 +182,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int img = mt / (tile_rows * tiles_per_row);
         const int rem = mt - img * (tile_rows * tiles_per_row);
@@ -201,7 +206,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
         tc_fence_after();
@@ -228,11 +233,28 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
     const bool accum = d.flags & MSG_CONV_ACCUM;
     const int hw = d.Hg * d.Wg;
-    uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);   // manual-flush slice of this warp
-    const int etid = tid - 64;                    // 0..127 within the epilogue group
-    uint32_t lt = 0, sgrp = 0;                    // tiles done, TMA-store groups issued
-    bool tma_pending = false;                     // (thread etid==0) bulk groups possibly still reading smem
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    // this warp's staging slice: 8 KB = two [32 rows x 128 B] TMA-store buffers (1024-byte aligned), also
+    // used as the skewed [32 x 144 B] tile of the manual flush
+    uint8_t* stage_w = stage_gen + q * 8192;
+    const uint32_t stage_w_s = sStage + q * 8192;
+    float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
+    for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
+    __syncwarp();
+    int stat_img = -1, stat_nt = -1, stat_cmax = 0;
+    auto flush_stats = [&]() {
+      if (stat_img >= 0) {
+        for (int c = lane; c < stat_cmax; c += 32) {
+          double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + stat_nt * BN + c) * 2;
+          atomicAdd(st, (double)wsum[c]);
+          atomicAdd(st + 1, (double)wsum[256 + c]);
+          wsum[c] = 0.f; wsum[256 + c] = 0.f;
+        }
+      }
+      __syncwarp();
+    };
+    uint32_t lt = 0, sgrp = 0;                    // tiles done, TMA-store groups issued by this warp
+    bool tma_pending = false;                     // (lane 0) bulk groups possibly still reading smem
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int buf = lt & 1;
       const long long m0 = (long long)mt * BM;
@@ -247,8 +269,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int gi = rem / d.Wg, gj = rem - gi * d.Wg;
         opix = (n * d.Ho + gi * d.out_stride + d.out_off_h) * d.Wo + gj * d.out_stride + d.out_off_w;
       }
-      const int opix0 = __shfl_sync(0xffffffffu, opix, 0) - q * 32;   // tstore: rows are consecutive pixels
+      const int opix_w = __shfl_sync(0xffffffffu, opix, 0);   // tstore: this warp's 32 rows are consecutive pixels
       const int n_img = (int)(m0 / hw);
+      if (do_stats && (n_img != stat_img || nt != stat_nt)) {
+        flush_stats();
+        stat_img = n_img; stat_nt = nt; stat_cmax = cmax;
+      }
       mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
@@ -270,25 +296,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (jj < ncol) v[jj] += __ldg(p.bias + co0 + cg + jj);
         }
         if (do_stats) {
+          // column sums of this warp's 32 rows, accumulated ON CHIP across the CTA's tiles (lane l owns
+          // column 32h+l of the group); flushed with fp64 atomics only when the image changes / at the end
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (h * 32 < ncol) {                  // uniform across the epilogue group
+            if (h * 32 < ncol) {
               float s1[32], s2[32];
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) { s1[jj] = v[h * 32 + jj]; s2[jj] = s1[jj] * s1[jj]; }
-              float cs = warp_transpose_reduce32(s1, lane);
-              float css = warp_transpose_reduce32(s2, lane);
-              red[(q * 2 + 0) * 32 + lane] = cs;
-              red[(q * 2 + 1) * 32 + lane] = css;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (etid < 32 && h * 32 + etid < ncol) {
-                float a = red[0 * 32 + etid] + red[2 * 32 + etid] + red[4 * 32 + etid] + red[6 * 32 + etid];
-                float b = red[1 * 32 + etid] + red[3 * 32 + etid] + red[5 * 32 + etid] + red[7 * 32 + etid];
-                double* st = p.stats + ((size_t)n_img * d.Co_total + d.co_off + co0 + cg + h * 32 + etid) * 2;
-                atomicAdd(st, (double)a);
-                atomicAdd(st + 1, (double)b);
-              }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              const float cs = warp_transpose_reduce32(s1, lane);
+              const float css = warp_transpose_reduce32(s2, lane);
+              wsum[cg + h * 32 + lane] += cs;
+              wsum[256 + cg + h * 32 + lane] += css;
             }
           }
         }
@@ -301,30 +320,31 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (jj < ncol)
               y[((size_t)n * d.Co_total + d.co_off + co0 + cg + jj) * plane + pp] = apply_act(v[jj], d.act);
         } else if (p.tstore && vec && !accum && ncol == 64) {
-          // ---- TMA store of a [128 rows x 64 cols] group through a 128B-swizzled staging buffer
+          // ---- per-warp TMA store of [32 rows x 64 cols] through a 128B-swizzled staging buffer: no
+          //      cross-warp barrier anywhere on the store path
           const uint32_t sb = sgrp & 1;
-          if (etid == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          uint8_t* dstrow = stage_gen + sb * (BM * 128) + row * 128;
+          if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          uint8_t* dstrow = stage_w + sb * 4096 + lane * 128;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
-            *reinterpret_cast<uint4*>(dstrow + ((g ^ (row & 7)) << 4)) = pack8(o);
+            *reinterpret_cast<uint4*>(dstrow + ((g ^ (lane & 7)) << 4)) = pack8(o);
           }
           fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (etid == 0) {
-            tma_store_2d(&mapC, sStage + sb * (BM * 128), d.co_off + co0 + cg, opix0);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapC, stage_w_s + sb * 4096, d.co_off + co0 + cg, opix_w);
             tma_pending = true;
           }
           ++sgrp;
         } else if (vec && (ncol == 64 || ncol == 32 || ncol == 16)) {
           // ---- manual flush: per-warp skewed staging, then 16-byte chunks, consecutive lanes along a row
           if (p.tstore) {                         // the TMA buffers alias this region: drain them first
-            if (etid == 0 && tma_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); tma_pending = false; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (lane == 0 && tma_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); tma_pending = false; }
+            __syncwarp();
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -370,7 +390,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
       }
     }
-    if (etid == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (do_stats) flush_stats();
+    if (lane == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -449,8 +470,9 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int K = d->KH * d->KW * d->Cin;
   const int stage_bytes = A_BYTES + p.BN * BK * 2;
-  const int fixed = STAGE_BYTES + 1024 + 8 * 16 + 64 + 1024;
-  p.tstore = (!(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
+  const int fixed = STAGE_BYTES + 8192 + 8 * 16 + 64 + 1024;
+  static const bool env_tstore = [] { const char* e = getenv("MSG_TMA_STORE"); return !(e && e[0] == '0'); }();
+  p.tstore = (env_tstore && !(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
               d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&
               (((uintptr_t)y) & 15) == 0) ? 1 : 0;
   int stages = (220 * 1024 - fixed) / stage_bytes;
@@ -486,7 +508,7 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   if (p.tstore) {
     cuuint64_t dims[2] = {(cuuint64_t)d->Co_total, (cuuint64_t)d->N * d->Ho * d->Wo};
     cuuint64_t strides[1] = {(cuuint64_t)d->Co_total * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BM};
+    cuuint32_t box[2] = {64, 32};   // one epilogue warp's rows
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mapC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,

@@ -14,7 +14,7 @@ Per stage (down1/down2/up1/up2, width C), kernels launched in the forward:
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, slab
 from .ops import ACT_NONE, ACT_RELU, ACT_TANH, ConvGeom
 
 STAGES = ("down1", "down2", "up1", "up2")
@@ -50,6 +50,23 @@ class GeneratorEngine:
                 g[f"{s}.4.branch{i}.0"] = ConvGeom("conv", C, C // 4, k, 1, p, d)
             g[f"{s}.4.fusion.0"] = ConvGeom("conv", C, C, 1)
         self._cache = {}
+        # row-slab programs (bf16 path, widths that are multiples of 64): fused MSB branches, 7x7 convs
+        self.use_slab = True
+        self._msb_prog = {C: slab.msb_program(C) for C in set(self.width.values()) if C % 64 == 0}
+        self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
+        self._out_prog = slab.conv7_out_program(c) if c % 64 == 0 else None
+
+    def _versions(self, params, names):
+        return tuple((params[n].data_ptr(), params[n]._version) for n in names)
+
+    def _slab_cached(self, params, key, names, build):
+        ver = self._versions(params, names)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        t = build()
+        self._cache[key] = (ver, t)
+        return t
 
     @staticmethod
     def edge_pad(dtype):
@@ -111,9 +128,18 @@ class GeneratorEngine:
             del att
         b = torch.empty_like(a1)
         stb = ops.new_stats(N, C, dev)
-        for i in range(1, 5):
-            n = f"{s}.4.branch{i}.0"
-            g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
+        if self.use_slab and dtype == torch.bfloat16 and C in self._msb_prog and a1.shape[2] % 8 == 0:
+            # one launch: 1x1 + 3x3 dil 1/2/4 branches share each input-row slab (csrc/conv_slab.cu)
+            prog = self._msb_prog[C]
+            wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
+            bn_ = [f"{s}.4.branch{i}.0.bias" for i in range(1, 5)]
+            wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb_weight_slab(prog, [P[k].detach() for k in wn]))
+            bsl = self._slab_cached(P, (s, "msb_b"), bn_, lambda: torch.cat([P[k].detach() for k in bn_]).contiguous())
+            slab.conv_slab(prog, a1, wsl, bsl, out=b, stats=stb)
+        else:
+            for i in range(1, 5):
+                n = f"{s}.4.branch{i}.0"
+                g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
         bn = ops.instnorm_apply(b, stb, ACT_RELU, out=None if keep else b)
         stf = ops.new_stats(N, C, dev)
         n = f"{s}.4.fusion.0"
@@ -135,7 +161,13 @@ class GeneratorEngine:
             raise RuntimeError(f"EnhancedGenerator: H and W must be multiples of 16, got {H}x{W}")
         x0 = ops.nchw_to_nhwc(x, dtype, self.edge_pad(dtype))
         sti = ops.new_stats(N, self.c, x.device)
-        yi = self._g("initial.0", dtype).forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
+        if self.use_slab and dtype == torch.bfloat16 and self._in_prog is not None and W % 8 == 0:
+            prog = self._in_prog
+            wsl = self._slab_cached(P, ("initial", "slab_w"), ["initial.0.weight"],
+                                    lambda: slab.conv7_in_weight_slab(prog, P["initial.0.weight"].detach()))
+            yi = slab.conv_slab(prog, x0, wsl, self._bias(P, "initial.0"), stats=sti)
+        else:
+            yi = self._g("initial.0", dtype).forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
         a = ops.instnorm_apply(yi, sti, ACT_RELU, out=None if save else yi)
         saved = {"x0": x0, "yi": yi, "sti": sti} if save else None
         for s in ("down1", "down2"):
@@ -155,8 +187,16 @@ class GeneratorEngine:
                 saved[s] = sv if save == "full" else {"a_in": a_in}
         N, H, W, _ = a.shape
         y = torch.empty((N, 3, H, W), device=a.device, dtype=torch.float32)
-        go = ConvGeom("conv", self.c, 3, 7, 1, 3)   # store 3 filters of the 4-row packed weight
-        go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0", dtype), act=ACT_TANH, nchw_out=y)
+        if self.use_slab and dtype == torch.bfloat16 and self._out_prog is not None and W % 8 == 0:
+            prog = self._out_prog
+            wsl = self._slab_cached(P, ("output", "slab_w"), ["output.0.weight"],
+                                    lambda: slab.conv7_out_weight_slab(prog, P["output.0.weight"].detach()))
+            bsl = self._slab_cached(P, ("output", "slab_b"), ["output.0.bias"],
+                                    lambda: _pad_dim(P["output.0.bias"].detach(), 0, 16).contiguous())
+            slab.conv_slab(prog, a, wsl, bsl, act=ACT_TANH, nchw_out=y)
+        else:
+            go = ConvGeom("conv", self.c, 3, 7, 1, 3)   # store 3 filters of the padded packed weight
+            go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0", dtype), act=ACT_TANH, nchw_out=y)
         if save:
             saved["a_last"] = a
             saved["y"] = y

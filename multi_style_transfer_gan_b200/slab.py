@@ -28,6 +28,7 @@ class SlabProgram:
         d.Cin, d.Ntot, d.n_store, d.ncols, d.halo, d.pixel_pair_k = (self.Cin, self.Ntot, self.n_store, self.ncols,
                                                                       self.halo, int(self.pixel_pair))
         d.n_kblocks, d.n_taps = len(self.kblocks), self.n_taps
+        d.n_chains = 1   # measured on B200: independent accumulation chains do not speed up small-N MMAs
         seen, tp = set(), 0
         for kb, (dy, cb, taps) in enumerate(self.kblocks):
             d.kb_dy[kb], d.kb_cb[kb], d.kb_tap_begin[kb] = dy, cb, tp
@@ -44,6 +45,7 @@ def msb_program(C):
     q = C // 4
     branches = [(1, 1), (3, 1), (3, 2), (3, 4)]   # (k, dilation) of branch1..4
     kblocks = []
+    max_taps = max(1, (64 * 1024) // (q * 128))          # keep a k-block's weight tiles <= 64 KB of smem
     for dy in (-4, -2, -1, 0, 1, 2, 4):
         for cb in range(C // 64):
             taps = []
@@ -53,7 +55,8 @@ def msb_program(C):
                         continue
                     for kw in range(k):
                         taps.append(((kw - k // 2) * dil, b * q, 0, (b, kh, kw, cb)))
-            kblocks.append((dy, cb, taps))
+            for i in range(0, len(taps), max_taps):          # a long tap list re-loads the slab (rare: C=256 centre row)
+                kblocks.append((dy, cb, taps[i:i + max_taps]))
     return SlabProgram(C, C, C, q, 4, False, kblocks)
 
 
