@@ -152,9 +152,14 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t sA = sB + (p.b_resident ? p.b_resident : S * p.b_bytes);
   const uint32_t sStage = (sA + S * p.a_bytes + 127u) & ~127u;
   const uint32_t sRed = sStage + 4 * 32 * STAGE_PITCH;        // per-warp column sums [4][2][256] floats
-  const uint32_t sBar = sRed + 8192;
+  const uint32_t sBias = sRed + 8192 + 4 * 1056 * 4;                         // bias staged once per CTA (Ntot <= 256 floats)
+  const uint32_t sBar = sBias + 1024;
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
+  float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
+  const bool bias_in_smem = p.bias != nullptr;
+  if (bias_in_smem)
+    for (int i = tid; i < d.Ntot; i += NTHREADS) sbias[i] = p.bias[i];
   const uint32_t wres_bar = sBar + 8u * (2 * S + 4);          // "resident weights have landed"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
@@ -267,7 +272,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int tp = t0; tp < t1; ++tp) {
             const uint64_t da = make_noswz_desc(a0 + (uint32_t)d.tap_sx[tp], 16u);
             const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);
-            const int chain = (tp - t0) % nch;              // 4 pair-taps per row -> up to 4 chains
+            const int chain = nch > 1 ? (tp - t0) % nch : 0;   // 4 pair-taps per row -> up to 4 chains
             if (elect_one())
               umma_bf16(tacc + (uint32_t)d.tap_acc_col[tp] + (uint32_t)(chain * d.Ntot), da, db, idesc, !(kb == 0 && (tp - t0) < nch));
           }
@@ -299,6 +304,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
     float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
+    float* tr = red + 2048 + q * 1056;            // [32][33] transpose scratch of this warp
     for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
     __syncwarp();
     int stat_img = -1;
@@ -348,22 +354,45 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
         if (p.bias != nullptr) {
+          if (bias_in_smem) {
 #pragma unroll
-          for (int jj = 0; jj < 64; ++jj)
-            if (jj < ncol) v[jj] += __ldg(p.bias + cg + jj);
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] += sbias[cg + jj];
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] += __ldg(p.bias + cg + jj);
+          }
         }
         if (do_stats) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 32 < ncol) {
-              float s1[32], s2[32];
+              // transpose this warp's 32 x 32 block through smem ([col][33]: conflict-free both ways); lane l
+              // then owns column l and sums its 32 rows (x and x^2) -- ~2x fewer instructions than shuffles
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) { s1[jj] = valid ? v[h * 32 + jj] : 0.f; s2[jj] = s1[jj] * s1[jj]; }
-              const float cs = warp_transpose_reduce32(s1, lane);
-              const float css = warp_transpose_reduce32(s2, lane);
+              for (int jj = 0; jj < 32; ++jj) tr[jj * 33 + lane] = valid ? v[h * 32 + jj] : 0.f;
+              __syncwarp();
+              float cs = 0.f, css = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
+              __syncwarp();
               wsum[cg + h * 32 + lane] += cs;
               wsum[256 + cg + h * 32 + lane] += css;
             }
+          }
+        }
+        if (d.act != MSG_ACT_NONE) {              // activation, switch hoisted out of the element loop
+          if (d.act == MSG_ACT_RELU) {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+          } else if (d.act == MSG_ACT_LRELU) {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj) v[jj] = v[jj] > 0.f ? v[jj] : 0.2f * v[jj];
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] = tanhf(v[jj]);
           }
         }
         if (nchw) {
@@ -374,7 +403,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int jj = 0; jj < 64; ++jj)
               if (jj < ncol)
-                y[((size_t)img * d.Co_total + d.co_off + cg + jj) * plane + pp] = apply_act(v[jj], d.act);
+                y[((size_t)img * d.Co_total + d.co_off + cg + jj) * plane + pp] = v[jj];
           }
         } else if (vec && (ncol == 64 || ncol == 32 || ncol == 16)) {
 #pragma unroll
@@ -382,7 +411,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (g * 8 < ncol) {
               float o[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+              for (int e = 0; e < 8; ++e) o[e] = v[g * 8 + e];
               *reinterpret_cast<uint4*>(stage_w + lane * STAGE_PITCH + g * 16) = pack8(o);
             }
           }
@@ -405,7 +434,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)opix * d.Co_total + d.co_off + cg;
 #pragma unroll
           for (int e = 0; e < 64; ++e)
-            if (e < ncol) y[e] = __float2bfloat16_rn(apply_act(v[e], d.act));
+            if (e < ncol) y[e] = __float2bfloat16_rn(v[e]);
         }
       }
     }
@@ -501,7 +530,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 256 + 1024 + p.b_resident;
+  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 4 * 1056 * 4 + 1024 + 256 + 1024 + p.b_resident;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_slab: stage of %d bytes does not fit twice in shared memory", stage_bytes);

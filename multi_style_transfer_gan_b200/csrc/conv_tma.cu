@@ -144,9 +144,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t sB = sA + S * A_BYTES;
   const uint32_t sStage = sB + S * b_bytes;                 // epilogue staging, 1024-byte aligned
   const uint32_t sRed = sStage + STAGE_BYTES;               // per-warp column sums [4][2][256] floats
-  const uint32_t sBar = sRed + 8192;                        // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t sBias = sRed + 8192 + 4 * 1056 * 4;                       // bias staged once per CTA (<= 1024 floats)
+  const uint32_t sBar = sBias + 4096;                       // full[S], empty[S], tfull[2], tempty[2]
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
+  float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
+  const bool bias_in_smem = p.bias != nullptr && d.Cout <= 1024;
+  if (bias_in_smem)
+    for (int i = tid; i < d.Cout; i += NTHREADS) sbias[i] = p.bias[i];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
@@ -238,6 +243,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t* stage_w = stage_gen + q * 8192;
     const uint32_t stage_w_s = sStage + q * 8192;
     float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
+    float* tr = red + 2048 + q * 1056;            // [32][33] transpose scratch of this warp
     for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
     __syncwarp();
     int stat_img = -1, stat_nt = -1, stat_cmax = 0;
@@ -291,9 +297,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
         if (p.bias != nullptr) {
+          if (bias_in_smem) {
 #pragma unroll
-          for (int jj = 0; jj < 64; ++jj)
-            if (jj < ncol) v[jj] += __ldg(p.bias + co0 + cg + jj);
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] += sbias[co0 + cg + jj];
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] += __ldg(p.bias + co0 + cg + jj);
+          }
         }
         if (do_stats) {
           // column sums of this warp's 32 rows, accumulated ON CHIP across the CTA's tiles (lane l owns
@@ -301,14 +313,31 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 32 < ncol) {
-              float s1[32], s2[32];
+              // transpose this warp's 32 x 32 block through smem ([col][33]: conflict-free both ways); lane l
+              // then owns column l and sums its 32 rows (x and x^2) -- ~2x fewer instructions than shuffles
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) { s1[jj] = v[h * 32 + jj]; s2[jj] = s1[jj] * s1[jj]; }
-              const float cs = warp_transpose_reduce32(s1, lane);
-              const float css = warp_transpose_reduce32(s2, lane);
+              for (int jj = 0; jj < 32; ++jj) tr[jj * 33 + lane] = v[h * 32 + jj];
+              __syncwarp();
+              float cs = 0.f, css = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
+              __syncwarp();
               wsum[cg + h * 32 + lane] += cs;
               wsum[256 + cg + h * 32 + lane] += css;
             }
+          }
+        }
+        if (d.act != MSG_ACT_NONE) {              // activation, switch hoisted out of the element loop
+          if (d.act == MSG_ACT_RELU) {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+          } else if (d.act == MSG_ACT_LRELU) {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj) v[jj] = v[jj] > 0.f ? v[jj] : 0.2f * v[jj];
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj)
+              if (jj < ncol) v[jj] = tanhf(v[jj]);
           }
         }
         if (nchw) {
@@ -318,7 +347,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int jj = 0; jj < 64; ++jj)
             if (jj < ncol)
-              y[((size_t)n * d.Co_total + d.co_off + co0 + cg + jj) * plane + pp] = apply_act(v[jj], d.act);
+              y[((size_t)n * d.Co_total + d.co_off + co0 + cg + jj) * plane + pp] = v[jj];
         } else if (p.tstore && vec && !accum && ncol == 64) {
           // ---- per-warp TMA store of [32 rows x 64 cols] through a 128B-swizzled staging buffer: no
           //      cross-warp barrier anywhere on the store path
@@ -330,7 +359,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           for (int g = 0; g < 8; ++g) {
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+            for (int e = 0; e < 8; ++e) o[e] = v[g * 8 + e];
             *reinterpret_cast<uint4*>(dstrow + ((g ^ (lane & 7)) << 4)) = pack8(o);
           }
           fence_proxy_async();
@@ -351,7 +380,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (g * 8 < ncol) {
               float o[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = apply_act(v[g * 8 + e], d.act);
+              for (int e = 0; e < 8; ++e) o[e] = v[g * 8 + e];
               *reinterpret_cast<uint4*>(stage_w + lane * STAGE_PITCH + g * 16) = pack8(o);
             }
           }
@@ -383,7 +412,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 64; ++e)
             if (e < ncol) {
-              float val = apply_act(v[e], d.act);
+              float val = v[e];
               if (accum) val += __bfloat162float(y[e]);
               y[e] = __float2bfloat16_rn(val);
             }
@@ -470,7 +499,7 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int K = d->KH * d->KW * d->Cin;
   const int stage_bytes = A_BYTES + p.BN * BK * 2;
-  const int fixed = STAGE_BYTES + 8192 + 8 * 16 + 64 + 1024;
+  const int fixed = STAGE_BYTES + 8192 + 4 * 1056 * 4 + 4096 + 8 * 16 + 64 + 1024;
   static const bool env_tstore = [] { const char* e = getenv("MSG_TMA_STORE"); return !(e && e[0] == '0'); }();
   p.tstore = (env_tstore && !(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
               d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&

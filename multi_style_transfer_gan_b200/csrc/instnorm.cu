@@ -141,6 +141,71 @@ in_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, long 
   }
 }
 
+// ---- apply, fast path (C power of two): activation / residual are template parameters, the channel
+// group of a thread is computed ONCE (no per-iteration 64-bit modulo), four independent 16-byte loads
+// are in flight per thread per iteration.
+template <typename T, int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(TPB)
+in_apply_fast_kernel(const T* __restrict__ x, const double* __restrict__ stats, long long HW, int C,
+                     const T* __restrict__ residual, int S, const float* __restrict__ gammas,
+                     const float* __restrict__ betas, const float* __restrict__ w, T* __restrict__ y) {
+  constexpr int W = Vec<T>::W;
+  constexpr int U = 4;
+  const int n = blockIdx.y;
+  const double inv_hw = 1.0 / (double)HW;
+  const size_t base = (size_t)n * HW * C;
+  const long long nvec = HW * C / W;
+  const long long stride = (long long)gridDim.x * TPB;
+  const long long v0 = (long long)blockIdx.x * TPB + threadIdx.x;
+  const int c0 = (int)((v0 * W) % C);          // loop-invariant: stride * W is a multiple of C
+  float scale[W], shift[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    const double* st = stats + ((size_t)n * C + c0 + e) * 2;
+    float mean, rstd;
+    finalize_stats(st[0], st[1], inv_hw, mean, rstd);
+    float g = 1.f, b = 0.f;
+    if (S > 0) {
+      g = 0.f;
+      for (int s = 0; s < S; ++s) {
+        g = fmaf(w[s], gammas[(size_t)s * C + c0 + e], g);
+        b = fmaf(w[s], betas[(size_t)s * C + c0 + e], b);
+      }
+    }
+    scale[e] = rstd * g;
+    shift[e] = b - mean * scale[e];
+  }
+  const T* xb = x + base;
+  const T* rb = HAS_RES ? residual + base : nullptr;
+  T* yb = y + base;
+  for (long long v = v0; v < nvec; v += U * stride) {
+    float t[U][W], r[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv < nvec) {
+        VecIO<W>::ld(xb + vv * W, t[u]);
+        if (HAS_RES) VecIO<W>::ld(rb + vv * W, r[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = v + u * stride;
+      if (vv < nvec) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          float o = fmaf(t[u][e], scale[e], shift[e]);
+          if (ACT == MSG_ACT_RELU) o = fmaxf(o, 0.f);
+          else if (ACT == MSG_ACT_LRELU) o = o > 0.f ? o : 0.2f * o;
+          if (HAS_RES) o += r[u][e];
+          t[u][e] = o;
+        }
+        VecIO<W>::st(yb + vv * W, t[u]);
+      }
+    }
+  }
+}
+
 // ---- backward -------------------------------------------------------------------------------
 // pass 1: scratch[n][c] += (sum g, sum g*xhat) with g = dy * act'(xhat)
 template <typename T, bool FAST>
@@ -287,8 +352,23 @@ template <typename T>
 int apply_impl(const T* x, const double* stats, int N, long long HW, int C, int act, const T* res,
                int S, const float* gammas, const float* betas, const float* w, T* y, cudaStream_t st) {
   if (fast_ok<T>(C, HW)) {
-    dim3 grid(blocks_per_image(N, HW * C / Vec<T>::W), N);
-    in_apply_kernel<T, true><<<grid, TPB, 0, st>>>(x, stats, HW, C, act, res, S, gammas, betas, w, y);
+    const long long nvec = HW * C / Vec<T>::W;
+    long long want = (4LL * sm_count() + N - 1) / N;           // ~4 CTAs per SM over the whole launch
+    long long maxb = (nvec + TPB * 4 - 1) / (TPB * 4);         // >= 4 vectors per thread
+    if (want > maxb) want = maxb;
+    if (want < 1) want = 1;
+    dim3 grid((unsigned)want, N);
+#define MSG_IN_APPLY(ACT, RES) in_apply_fast_kernel<T, ACT, RES><<<grid, TPB, 0, st>>>(x, stats, HW, C, res, S, gammas, betas, w, y)
+    if (res) {
+      if (act == MSG_ACT_RELU) MSG_IN_APPLY(MSG_ACT_RELU, true);
+      else if (act == MSG_ACT_LRELU) MSG_IN_APPLY(MSG_ACT_LRELU, true);
+      else MSG_IN_APPLY(MSG_ACT_NONE, true);
+    } else {
+      if (act == MSG_ACT_RELU) MSG_IN_APPLY(MSG_ACT_RELU, false);
+      else if (act == MSG_ACT_LRELU) MSG_IN_APPLY(MSG_ACT_LRELU, false);
+      else MSG_IN_APPLY(MSG_ACT_NONE, false);
+    }
+#undef MSG_IN_APPLY
   } else {
     dim3 grid(blocks_per_image(N, HW * C), N);
     in_apply_kernel<T, false><<<grid, TPB, 0, st>>>(x, stats, HW, C, act, res, S, gammas, betas, w, y);

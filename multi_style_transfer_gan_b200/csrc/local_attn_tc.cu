@@ -191,7 +191,7 @@ int launch(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* out, cu
   cudaError_t e = cudaFuncSetAttribute(local_attn_fwd_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "local_attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const long long nwin = (long long)N * (H / 4) * (W / 4);
-  const int per_sm = C >= 256 ? 2 : 4;
+  const int per_sm = C >= 256 ? 3 : (C >= 128 ? 4 : 8);   // resident CTAs per SM (smem / register limits)
   long long grid = (long long)per_sm * sm_count();
   if (grid > nwin) grid = nwin;
   local_attn_fwd_tc_kernel<C><<<(unsigned)grid, LT_THREADS, smem, st>>>(qkv, N, H, W, out);

@@ -22,6 +22,16 @@ from .enhanced_generator import EnhancedDiscriminator, EnhancedGenerator
 from .losses import l1, mse_to_const
 
 
+def allreduce_flat_(flat_grad):
+    """Data-parallel gradient exchange: ONE sum all-reduce over the flat gradient buffer (NCCL over
+    NVLink on the GPUs; any initialised backend works).  Returns the scale (1/world) the fused Adam
+    folds into its update.  No-op (returns 1.0) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas=(0.5,0.999), eps=1e-8) semantics (enhanced_train.py:36-43) as one
     kernel launch over a flat parameter / gradient buffer.  Parameters are re-pointed to views of
@@ -99,10 +109,7 @@ class EnhancedCycleGAN:
             m.invalidate_packed_weights()
 
     def _sync_grads(self, opt):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)   # one flat NCCL all-reduce
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        return allreduce_flat_(opt.flat_grad)
 
     def train_step(self, real_A, real_B):
         """reference: enhanced_train.py:59-131 (order of the 6 G and 10 D forwards preserved, so the
