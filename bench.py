@@ -224,12 +224,12 @@ def run_ours(args):
         # roofline of the dominant kernel family (tcgen05 conv): algorithmic conv FLOPs of the step
         # divided by the summed CUDA-event time of its launches inside the timed region.
         scale = (H * W) / 512 ** 2
-        conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in ("msg_conv2d", "msg_conv_slab")) / args.steps
-        conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in ("msg_conv2d", "msg_conv_slab")) // args.steps
+        conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in ("msg_conv2d", "msg_conv_slab", "msg_conv_shift")) / args.steps
+        conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in ("msg_conv2d", "msg_conv_slab", "msg_conv_shift")) // args.steps
         flops = 3 * B * CONV_GFLOP_512 * scale * 1e9
         if conv_ms > 0:
             ach = flops / (conv_ms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_tma_kernel + conv_slab_kernel (every conv / convT launch of the step)",
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_tma_kernel + conv_slab_kernel + conv_shift_kernel (every conv / convT launch of the step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                                 "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",

@@ -130,6 +130,37 @@ typedef struct {
 int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* w_slab, const float* bias, void* y,
                   double* stats, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * "Taps-as-N" row-slab convolution (bf16, Cin % 64 == 0): all filter taps sharing an input row are ONE
+ * MMA (filters stacked along N over the unshifted slab); the horizontal shifts are applied in the
+ * epilogue.  Used for the 7x7 output conv (enhanced_generator.py:137) and the fused MultiScaleBlock
+ * branches at C = 64 (:52-71).  k-block kb: slab row y + kb_dy, channel block kb_cb, weight rows
+ * [kb_wrow, kb_wrow + kb_ncols) of w_rows ([rows][64] bf16) -> accumulator columns [kb_col0, +kb_ncols).
+ * Output group g:  out[x][grp_out_col0 + c] = sum_{terms} acc[x + term_shift][grp_col0 + term_col + c],
+ * c < grp_out_cols (<= 16), x in [0, 128 - 2*halo).
+ * ------------------------------------------------------------------------------------------- */
+#define MSG_SHIFT_MAX_KBLOCKS 32
+#define MSG_SHIFT_MAX_GROUPS 8
+#define MSG_SHIFT_MAX_TERMS 32
+typedef struct {
+  int dtype;
+  int N, H, W, Ci_total, ci_off, Cin;
+  int Co_total, co_off;
+  int Ntot;        /* accumulator columns (multiple of 16, <= 256)  */
+  int n_out;       /* output columns (<= 64); bias / stats indexing */
+  int halo;
+  int act;
+  unsigned flags;  /* MSG_CONV_STATS | MSG_CONV_OUT_NCHW_F32 */
+  int n_kblocks, n_groups, n_terms;
+  int kb_dy[MSG_SHIFT_MAX_KBLOCKS], kb_cb[MSG_SHIFT_MAX_KBLOCKS], kb_col0[MSG_SHIFT_MAX_KBLOCKS],
+      kb_ncols[MSG_SHIFT_MAX_KBLOCKS], kb_wrow[MSG_SHIFT_MAX_KBLOCKS], kb_first[MSG_SHIFT_MAX_KBLOCKS];
+  int grp_col0[MSG_SHIFT_MAX_GROUPS], grp_span[MSG_SHIFT_MAX_GROUPS], grp_out_col0[MSG_SHIFT_MAX_GROUPS],
+      grp_out_cols[MSG_SHIFT_MAX_GROUPS], grp_term_begin[MSG_SHIFT_MAX_GROUPS + 1];
+  int term_shift[MSG_SHIFT_MAX_TERMS], term_col[MSG_SHIFT_MAX_TERMS];
+} msg_shift_desc;
+int msg_conv_shift(const msg_shift_desc* d, const void* x, const void* w_rows, const float* bias, void* y,
+                   double* stats, void* stream);
+
 /* wgrad of the same descriptor: dw[co][th][tw][ci] (fp32, packed layout, ACCUMULATED into) =
  * sum over pixels of dy[..., co] * gathered x[..., ci].  Replaces autograd's conv weight grads for
  * every conv above (enhanced_train.py:84,121). */

@@ -40,6 +40,20 @@ class SlabDesc(ctypes.Structure):
         ("tap_first", c_int * SLAB_MAX_TAPS), ("tap_kstep", c_int * SLAB_MAX_TAPS)]
 
 
+SHIFT_MAX_KBLOCKS, SHIFT_MAX_GROUPS, SHIFT_MAX_TERMS = 32, 8, 32
+
+
+class ShiftDesc(ctypes.Structure):
+    """mirrors msg_shift_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in (
+        "dtype", "N", "H", "W", "Ci_total", "ci_off", "Cin", "Co_total", "co_off", "Ntot", "n_out", "halo", "act")] + [
+        ("flags", c_uint), ("n_kblocks", c_int), ("n_groups", c_int), ("n_terms", c_int)] + [
+        (n, c_int * SHIFT_MAX_KBLOCKS) for n in ("kb_dy", "kb_cb", "kb_col0", "kb_ncols", "kb_wrow", "kb_first")] + [
+        (n, c_int * SHIFT_MAX_GROUPS) for n in ("grp_col0", "grp_span", "grp_out_col0", "grp_out_cols")] + [
+        ("grp_term_begin", c_int * (SHIFT_MAX_GROUPS + 1)),
+        ("term_shift", c_int * SHIFT_MAX_TERMS), ("term_col", c_int * SHIFT_MAX_TERMS)]
+
+
 _P = c_void_p
 # name -> argtypes (everything returns int except msg_last_error)
 SIGNATURES = {
@@ -49,6 +63,7 @@ SIGNATURES = {
     "msg_conv2d": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "msg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
     "msg_conv_slab": [ctypes.POINTER(SlabDesc), _P, _P, _P, _P, _P, _P],
+    "msg_conv_shift": [ctypes.POINTER(ShiftDesc), _P, _P, _P, _P, _P, _P],
     "msg_pack_conv_weight": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_unpack_conv_wgrad": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "msg_bias_grad": [c_int, _P, c_ll, c_int, c_int, c_int, _P, _P],

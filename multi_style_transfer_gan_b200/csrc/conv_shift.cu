@@ -1,0 +1,442 @@
+// "Taps-as-N" row-slab convolution (sm_100a, bf16): stride-1 same-size convs whose per-tap N is tiny.
+//
+// A tcgen05.mma with M=128, K=16 costs ~90 cycles on B200 almost independently of N when N <= 64
+// (measured: the A-operand fetch dominates), so issuing one N=16 MMA per filter tap (conv_slab.cu)
+// leaves the tensor core ~10x under-used.  Here ALL taps that share an input-row slab are ONE MMA:
+// the slab is the UNSHIFTED A operand [128 slab pixels x 64 ch], the taps' filters are stacked along N
+// (7 taps x 4 padded filters = 32 columns for the 7x7 output conv; 1 + 3x3 (branch, sx) column groups
+// of 16 = 160 columns for the MultiScaleBlock at C=64), giving partial products
+//      D'[p][tap cols] = sum_c slab[p][c] * W_tap[c]        for every slab pixel p,
+// and the horizontal tap shift is applied in the EPILOGUE:  out[x][c] = sum_taps D'[x + shift_tap][col_tap + c]
+// through a shared-memory exchange tile (rows = slab pixels).  A tile yields 128 - 2*halo outputs.
+// MMAs per tile: (filter rows) x (Cin/16) instead of (taps) x (Cin/16): 28 instead of 196 for the 7x7.
+//
+// Pipeline: warp 0 TMA producer (weights resident in smem, loaded once; one 128B-swizzled slab box per
+// k-block), warp 1 MMA issuer (warp-uniform loop, elected lane), warps 2-5 epilogue, double-buffered TMEM.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace msg {
+namespace {
+
+constexpr int BM = 128;
+constexpr int NTHREADS = 192;
+constexpr int A_BYTES = BM * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct ShiftParams {
+  msg_shift_desc d;
+  const float* bias;
+  void* y;
+  double* stats;
+  int stages, tmem_cols, b_bytes, b_rows, Wv, segs, ex_pitch;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const ShiftParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const msg_shift_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sB = base;                                   // resident weights [b_rows][128 B], SW128
+  const uint32_t sA = sB + p.b_bytes;                         // slab ring
+  const uint32_t sEx = sA + S * A_BYTES;                      // exchange tile [128][Ntot + 4] floats
+  const uint32_t sSum = sEx + BM * p.ex_pitch * 4;              // per-warp column sums [4][2][64] floats
+  const uint32_t sTr = sSum + 4 * 128 * 4;                    // per-warp transpose scratch [4][32][33]
+  const uint32_t sBias = sTr + 4 * 1056 * 4;                  // bias [<= 256]
+  const uint32_t sBar = (sBias + 1024 + 7u) & ~7u;
+  float* ex = reinterpret_cast<float*>(gen + (sEx - base));
+  float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return sBar + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return sBar + 8u * (2 * S + 2 + b); };
+  const uint32_t wres_bar = sBar + 8u * (2 * S + 4);
+
+  if (p.bias != nullptr)
+    for (int i = tid; i < d.n_out; i += NTHREADS) sbias[i] = p.bias[i];
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+      mbar_init(wres_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = d.N * d.H * p.segs;
+  const int t_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(wres_bar, (uint32_t)p.b_bytes);          // weights: once, boxes of 32 rows
+      for (int r = 0; r < p.b_rows; r += 32) tma_load_2d(sB + r * 128, &mapB, wres_bar, 0, r);
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int seg = t % p.segs, ny = t / p.segs;
+        const int yrow = ny % d.H, img = ny / d.H;
+        const int x0 = seg * p.Wv - d.halo;
+        for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
+          const int s = it % S;
+          if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+          mbar_expect_tx(full_bar(s), A_BYTES);
+          tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), d.kb_cb[kb] * 64, x0, yrow + d.kb_dy[kb], img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (warp-uniform, elected lane issues) =============
+    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
+    const uint64_t sw128_hi = make_sw128_desc(0);
+    uint32_t it = 0, lt = 0;
+    mbar_wait(wres_bar, 0);
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
+      const int buf = lt & 1;
+      if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot);
+      for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
+        tc_fence_after();
+        const uint64_t da = sw128_hi | (uint64_t)((sA + s * A_BYTES) >> 4);
+        const uint64_t db = sw128_hi | (uint64_t)((sB + (uint32_t)d.kb_wrow[kb] * 128u) >> 4);
+        const uint32_t idesc = idesc0 | ((uint32_t)(d.kb_ncols[kb] >> 3) << 17);
+        const uint32_t dcol = tacc + (uint32_t)d.kb_col0[kb];
+        const uint32_t first = (uint32_t)d.kb_first[kb];
+        if (elect_one()) {
+          umma_bf16(dcol, da, db, idesc, !first);
+          umma_bf16(dcol, da + 2, db + 2, idesc, 1);
+          umma_bf16(dcol, da + 4, db + 4, idesc, 1);
+          umma_bf16(dcol, da + 6, db + 6, idesc, 1);
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+      if (elect_one()) umma_commit(tfull_bar(buf));
+    }
+  } else {
+    // ===================================== epilogue (warps 2-5) =====================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                // slab pixel held by this thread (TMEM lane)
+    const bool do_stats = d.flags & MSG_CONV_STATS;
+    const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
+    float* wsum = reinterpret_cast<float*>(gen + (sSum - base)) + q * 128;    // [2][64]
+    float* tr = reinterpret_cast<float*>(gen + (sTr - base)) + q * 1056;      // [32][33]
+    for (int i = lane; i < 128; i += 32) wsum[i] = 0.f;
+    __syncwarp();
+    int stat_img = -1;
+    auto flush_stats = [&]() {
+      if (stat_img >= 0) {
+        for (int c = lane; c < d.n_out; c += 32) {
+          double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
+          atomicAdd(st, (double)wsum[c]);
+          atomicAdd(st + 1, (double)wsum[64 + c]);
+          wsum[c] = 0.f; wsum[64 + c] = 0.f;
+        }
+      }
+      __syncwarp();
+    };
+    uint32_t lt = 0;
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
+      const int seg = t % p.segs, ny = t / p.segs;
+      const int yrow = ny % d.H, img = ny / d.H;
+      const int buf = lt & 1;
+      const int xcol = seg * p.Wv + row;                      // output column of this thread (if row < Wv)
+      const bool valid = row < p.Wv && xcol < d.W;
+      const size_t opix = ((size_t)img * d.H + yrow) * d.W + (valid ? xcol : 0);
+      if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
+      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot) + ((uint32_t)(q * 32) << 16);
+      // ---- phase 1: every accumulator column of this thread's slab pixel -> exchange tile (float4 stores;
+      //      pitch = Ntot + 4 floats keeps row-per-lane 128-bit accesses conflict-free)
+      float* exrow = ex + row * p.ex_pitch;
+      for (int c0 = 0; c0 < d.Ntot; c0 += 32) {
+        __syncwarp();
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= d.Ntot) {                              // accumulator fully read: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + 4 * i < d.Ntot)
+            *reinterpret_cast<float4*>(exrow + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- phase 2: out[x][c] = sum_terms ex[x + shift][col + c], then bias / stats / activation / store
+      for (int g = 0; g < d.n_groups; ++g) {
+        const int oc = d.grp_out_cols[g];                     // <= 16
+        const int oc0 = d.grp_out_col0[g];
+        float o[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[c] = 0.f;
+        if (row < p.Wv) {
+          for (int tm = d.grp_term_begin[g]; tm < d.grp_term_begin[g + 1]; ++tm) {
+            const float* src = ex + (row + d.term_shift[tm]) * p.ex_pitch + d.grp_col0[g] + d.term_col[tm];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              if (c4 * 4 < oc) {
+                const float4 f = *reinterpret_cast<const float4*>(src + 4 * c4);
+                o[4 * c4] += f.x; o[4 * c4 + 1] += f.y; o[4 * c4 + 2] += f.z; o[4 * c4 + 3] += f.w;
+              }
+            }
+          }
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < oc) o[c] += sbias[oc0 + c];
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) tr[c * 33 + lane] = (valid && c < oc) ? o[c] : 0.f;
+          __syncwarp();
+          if (lane < 16) {
+            float cs = 0.f, css = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
+            if (lane < oc) { wsum[oc0 + lane] += cs; wsum[64 + oc0 + lane] += css; }
+          }
+          __syncwarp();
+        }
+        if (d.act == MSG_ACT_RELU) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = fmaxf(o[c], 0.f);
+        } else if (d.act == MSG_ACT_LRELU) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = o[c] > 0.f ? o[c] : 0.2f * o[c];
+        } else if (d.act == MSG_ACT_TANH) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < oc) o[c] = tanhf(o[c]);
+        }
+        if (valid) {
+          if (nchw) {
+            float* y = reinterpret_cast<float*>(p.y);
+            const size_t plane = (size_t)d.H * d.W;
+            const size_t pp = (size_t)yrow * d.W + xcol;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (c < oc) y[((size_t)img * d.Co_total + d.co_off + oc0 + c) * plane + pp] = o[c];
+          } else {
+            __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * d.Co_total + d.co_off + oc0;
+            if (oc == 16 && ((d.Co_total | d.co_off | oc0) & 7) == 0) {
+              float lo[8], hi[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) { lo[c] = o[c]; hi[c] = o[8 + c]; }
+              *reinterpret_cast<uint4*>(y) = pack8(lo);
+              *reinterpret_cast<uint4*>(y + 8) = pack8(hi);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < oc) y[c] = __float2bfloat16_rn(o[c]);
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // exchange tile free for the next tile
+    }
+    if (do_stats) flush_stats();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+}  // namespace msg
+
+using namespace msg;
+
+extern "C" int msg_conv_shift(const msg_shift_desc* d, const void* x, const void* w_rows, const float* bias,
+                              void* y, double* stats, void* stream) {
+  MSG_REQUIRE(d != nullptr, MSG_ERR_SHAPE, "conv_shift: null descriptor");
+  MSG_REQUIRE(d->dtype == MSG_BF16, MSG_ERR_UNSUPPORTED, "conv_shift: bf16 only");
+  MSG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, MSG_ERR_SHAPE, "conv_shift: bad plane");
+  MSG_REQUIRE(d->Cin % 64 == 0 && (d->Ci_total & 7) == 0 && (d->ci_off & 7) == 0, MSG_ERR_SHAPE, "conv_shift: channel layout unsupported");
+  MSG_REQUIRE(d->Ntot % 16 == 0 && d->Ntot >= 16 && d->Ntot <= 256 && d->n_out >= 1 && d->n_out <= 64, MSG_ERR_SHAPE, "conv_shift: bad N configuration");
+  MSG_REQUIRE(d->halo >= 0 && d->halo <= 16 && d->n_kblocks >= 1 && d->n_kblocks <= MSG_SHIFT_MAX_KBLOCKS &&
+                  d->n_groups >= 1 && d->n_groups <= MSG_SHIFT_MAX_GROUPS && d->n_terms <= MSG_SHIFT_MAX_TERMS,
+              MSG_ERR_SHAPE, "conv_shift: program too large");
+  MSG_REQUIRE((((uintptr_t)x | (uintptr_t)w_rows) & 15) == 0, MSG_ERR_ALIGN, "conv_shift: operands must be 16-byte aligned");
+  MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv_shift: stats buffer missing");
+  int rows = 0;
+  for (int kb = 0; kb < d->n_kblocks; ++kb) {
+    MSG_REQUIRE(d->kb_ncols[kb] >= 16 && d->kb_ncols[kb] % 16 == 0 && d->kb_col0[kb] >= 0 &&
+                    d->kb_col0[kb] + d->kb_ncols[kb] <= d->Ntot && d->kb_wrow[kb] % 8 == 0,
+                MSG_ERR_SHAPE, "conv_shift: bad k-block %d", kb);
+    if (d->kb_wrow[kb] + d->kb_ncols[kb] > rows) rows = d->kb_wrow[kb] + d->kb_ncols[kb];
+  }
+  for (int g = 0; g < d->n_groups; ++g)
+    MSG_REQUIRE(d->grp_span[g] >= 1 && d->grp_span[g] <= 64 && d->grp_out_cols[g] >= 1 && d->grp_out_cols[g] <= 16 &&
+                    d->grp_col0[g] >= 0 && d->grp_col0[g] + d->grp_span[g] <= d->Ntot,
+                MSG_ERR_SHAPE, "conv_shift: bad group %d", g);
+  EncodeTiledFn enc = get_encode();
+  MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "conv_shift: cuTensorMapEncodeTiled unavailable");
+
+  ShiftParams p;
+  p.d = *d; p.bias = bias; p.y = y; p.stats = stats;
+  p.b_rows = (rows + 31) / 32 * 32;
+  p.b_bytes = p.b_rows * 128;
+  MSG_REQUIRE(p.b_bytes <= 100 * 1024, MSG_ERR_UNSUPPORTED, "conv_shift: %d bytes of weights do not fit in shared memory", p.b_bytes);
+  p.Wv = BM - 2 * d->halo;
+  p.segs = (d->W + p.Wv - 1) / p.Wv;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * ((d->Ntot + 31) / 32 * 32)) p.tmem_cols <<= 1;
+  MSG_REQUIRE(p.tmem_cols <= 512, MSG_ERR_SHAPE, "conv_shift: accumulator too wide");
+  for (int g = 0; g < d->n_groups; ++g)   // the epilogue reads whole 32-column chunks: keep them inside the allocation
+    MSG_REQUIRE(d->Ntot + d->grp_col0[g] + ((d->grp_span[g] + 31) / 32) * 32 <= p.tmem_cols, MSG_ERR_SHAPE,
+                "conv_shift: group %d reads past the TMEM allocation", g);
+  p.ex_pitch = ((d->Ntot + 3) / 4) * 4 + 4;      // 16-byte aligned rows, pitch % 32 floats == 4: conflict-free float4 access
+  if (p.ex_pitch % 32 != 4) p.ex_pitch += (4 - p.ex_pitch % 32 + 32) % 32;
+  const int fixed = p.b_bytes + BM * p.ex_pitch * 4 + 4 * 128 * 4 + 4 * 1056 * 4 + 1024 + 256 + 1024;
+  int stages = (220 * 1024 - fixed) / A_BYTES;
+  if (stages > 8) stages = 8;
+  MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_shift: not enough shared memory for the slab ring");
+  p.stages = stages;
+  const size_t smem = (size_t)stages * A_BYTES + fixed;
+
+  CUtensorMap mapA, mapB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->W * d->Ci_total * 2,
+                             (cuuint64_t)d->H * d->W * d->Ci_total * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BM, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    void* base = (void*)((const __nv_bfloat16*)x + d->ci_off);
+    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_shift: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_rows, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_shift: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_shift: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  const long long total = (long long)d->N * d->H * p.segs;
+  MSG_REQUIRE(total < 0x7fffffffLL, MSG_ERR_SHAPE, "conv_shift: too many tiles");
+  if (grid > total) grid = (int)total;
+  conv_shift_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(mapA, mapB, p);
+  return check_launch("conv_shift_kernel");
+}

@@ -54,7 +54,8 @@ class GeneratorEngine:
         self.use_slab = True
         self._msb_prog = {C: slab.msb_program(C) for C in set(self.width.values()) if C % 64 == 0}
         self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
-        self._out_prog = slab.conv7_out_program(c) if c % 64 == 0 else None
+        self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
+        self._msb64_prog = slab.msb64_shift_program()
 
     def _versions(self, params, names):
         return tuple((params[n].data_ptr(), params[n]._version) for n in names)
@@ -129,13 +130,17 @@ class GeneratorEngine:
         b = torch.empty_like(a1)
         stb = ops.new_stats(N, C, dev)
         if self.use_slab and dtype == torch.bfloat16 and C in self._msb_prog and a1.shape[2] % 8 == 0:
-            # one launch: 1x1 + 3x3 dil 1/2/4 branches share each input-row slab (csrc/conv_slab.cu)
-            prog = self._msb_prog[C]
+            # one launch for the 1x1 + 3x3 dil 1/2/4 branches: they share each input-row slab
             wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
             bn_ = [f"{s}.4.branch{i}.0.bias" for i in range(1, 5)]
-            wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb_weight_slab(prog, [P[k].detach() for k in wn]))
             bsl = self._slab_cached(P, (s, "msb_b"), bn_, lambda: torch.cat([P[k].detach() for k in bn_]).contiguous())
-            slab.conv_slab(prog, a1, wsl, bsl, out=b, stats=stb)
+            if C == 64:     # taps-as-N: one MMA per (input row, K step), shifts applied in the epilogue (conv_shift.cu)
+                wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb64_shift_weights([P[k].detach() for k in wn]))
+                slab.conv_shift(self._msb64_prog, a1, wsl, bsl, out=b, stats=stb)
+            else:           # one MMA per tap on shifted views of the slab (conv_slab.cu)
+                prog = self._msb_prog[C]
+                wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb_weight_slab(prog, [P[k].detach() for k in wn]))
+                slab.conv_slab(prog, a1, wsl, bsl, out=b, stats=stb)
         else:
             for i in range(1, 5):
                 n = f"{s}.4.branch{i}.0"
@@ -190,10 +195,8 @@ class GeneratorEngine:
         if self.use_slab and dtype == torch.bfloat16 and self._out_prog is not None and W % 8 == 0:
             prog = self._out_prog
             wsl = self._slab_cached(P, ("output", "slab_w"), ["output.0.weight"],
-                                    lambda: slab.conv7_out_weight_slab(prog, P["output.0.weight"].detach()))
-            bsl = self._slab_cached(P, ("output", "slab_b"), ["output.0.bias"],
-                                    lambda: _pad_dim(P["output.0.bias"].detach(), 0, 16).contiguous())
-            slab.conv_slab(prog, a, wsl, bsl, act=ACT_TANH, nchw_out=y)
+                                    lambda: slab.conv7_out_shift_weights(prog, P["output.0.weight"].detach()))
+            slab.conv_shift(prog, a, wsl, P["output.0.bias"].detach().contiguous(), act=ACT_TANH, nchw_out=y)
         else:
             go = ConvGeom("conv", self.c, 3, 7, 1, 3)   # store 3 filters of the padded packed weight
             go.forward(a, self._packed(P, "output.0", "fwd", dtype), self._bias(P, "output.0", dtype), act=ACT_TANH, nchw_out=y)

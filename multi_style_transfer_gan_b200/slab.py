@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS, SlabDesc
+from ._lib import SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS, ShiftDesc, SlabDesc
 
 
 class SlabProgram:
@@ -125,5 +125,96 @@ def conv_slab(prog, x, w_slab, bias, out=None, co_off=0, stats=None, act=ops.ACT
         y, d.Co_total = out, out.shape[3]
     d.co_off, d.act, d.flags = co_off, act, flags
     _lib.call("msg_conv_slab", ctypes.byref(d), ops._p(x), ops._p(w_slab), ops._p(bias), ops._p(y), ops._p(stats),
+              ops._stream())
+    return nchw_out if nchw_out is not None else out
+
+
+# --------------------------------------------------------------------------------------------------
+# "taps-as-N" programs (csrc/conv_shift.cu)
+# --------------------------------------------------------------------------------------------------
+class ShiftProgram:
+    def __init__(self, Cin, Ntot, n_out, halo, kblocks, groups):
+        """kblocks: [(dy, cb, col0, ncols, wrow)] (the first one must cover every accumulator column: it
+        overwrites, the others accumulate); groups: [(col0, span, out_col0, out_cols, [(shift, col), ...])]"""
+        self.Cin, self.Ntot, self.n_out, self.halo, self.kblocks, self.groups = Cin, Ntot, n_out, halo, kblocks, groups
+        assert kblocks[0][2] == 0 and kblocks[0][3] == Ntot
+
+    def fill(self, d):
+        d.Cin, d.Ntot, d.n_out, d.halo = self.Cin, self.Ntot, self.n_out, self.halo
+        d.n_kblocks, d.n_groups = len(self.kblocks), len(self.groups)
+        for i, (dy, cb, col0, ncols, wrow) in enumerate(self.kblocks):
+            d.kb_dy[i], d.kb_cb[i], d.kb_col0[i], d.kb_ncols[i], d.kb_wrow[i], d.kb_first[i] = dy, cb, col0, ncols, wrow, int(i == 0)
+        t = 0
+        for g, (col0, span, oc0, oc, terms) in enumerate(self.groups):
+            d.grp_col0[g], d.grp_span[g], d.grp_out_col0[g], d.grp_out_cols[g], d.grp_term_begin[g] = col0, span, oc0, oc, t
+            for shift, col in terms:
+                d.term_shift[t], d.term_col[t] = shift, col
+                t += 1
+        d.grp_term_begin[len(self.groups)] = t
+        d.n_terms = t
+
+
+def conv7_out_shift_program(c):
+    """7x7 c->3 conv: per filter row ONE N=32 MMA (7 taps x 4 padded filters); 28*c/64 MMAs per tile."""
+    CB = c // 64
+    kblocks = [(kh - 3, cb, 0, 32, (kh * CB + cb) * 32) for kh in range(7) for cb in range(CB)]
+    groups = [(0, 28, 0, 3, [(kw, kw * 4) for kw in range(7)])]
+    return ShiftProgram(c, 32, 3, 3, kblocks, groups)
+
+
+def conv7_out_shift_weights(prog, w, dtype=torch.bfloat16):
+    """w [3, c, 7, 7] fp32 -> [7*CB*32, 64]: row (kh, cb, kw*4 + co) = w[co, cb*64:(cb+1)*64, kh, kw]."""
+    c = w.shape[1]
+    CB = c // 64
+    t = torch.zeros(7, CB, 8, 4, 64, device=w.device, dtype=torch.float32)
+    # w[co, cb*64+k, kh, kw] -> t[kh, cb, kw, co, k]
+    t[:, :, :7, :3] = w.reshape(3, CB, 64, 7, 7).permute(3, 1, 4, 0, 2)
+    return t.reshape(7 * CB * 32, 64).to(dtype).contiguous()
+
+
+def msb64_shift_program():
+    """MultiScaleBlock branches at C=64 (q=16): accumulator columns = b1 [0,16) | b2 sx=-1,0,1 [16,64) |
+    b3 sx=-2,0,2 [64,112) | b4 sx=-4,0,4 [112,160).  Centre row first (N=160), then the six other rows (N=48)."""
+    kblocks = [(0, 0, 0, 160, 0)]
+    wrow = 160
+    for b, dil in ((1, 1), (2, 2), (3, 4)):
+        for kh in (0, 2):
+            kblocks.append(((kh - 1) * dil, 0, 16 + 48 * (b - 1), 48, wrow))
+            wrow += 48
+    groups = [(0, 16, 0, 16, [(4, 0)])]
+    for b, dil in ((1, 1), (2, 2), (3, 4)):
+        groups.append((16 + 48 * (b - 1), 48, 16 * b, 16, [(4 - dil, 0), (4, 16), (4 + dil, 32)]))
+    return ShiftProgram(64, 160, 64, 4, kblocks, groups)
+
+
+def msb64_shift_weights(weights, dtype=torch.bfloat16):
+    """weights: [w1 [16,64,1,1], w2..w4 [16,64,3,3]] fp32 -> [448, 64] in the program's row order."""
+    rows = [weights[0][:, :, 0, 0]]
+    for b in (1, 2, 3):
+        rows += [weights[b][:, :, 1, kw] for kw in range(3)]          # centre filter row
+    for b in (1, 2, 3):
+        for kh in (0, 2):
+            rows += [weights[b][:, :, kh, kw] for kw in range(3)]
+    return torch.cat(rows, 0).to(dtype).contiguous()
+
+
+def conv_shift(prog, x, w_rows, bias, out=None, co_off=0, stats=None, act=ops.ACT_NONE, nchw_out=None, ci_off=0):
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    d = ShiftDesc()
+    d.dtype, d.N, d.H, d.W, d.Ci_total, d.ci_off = _lib.BF16, N, H, W, Ci_total, ci_off
+    prog.fill(d)
+    flags = 0
+    if stats is not None:
+        flags |= _lib.CONV_STATS
+    if nchw_out is not None:
+        flags |= _lib.CONV_OUT_NCHW_F32
+        y, d.Co_total = nchw_out, prog.n_out
+    else:
+        if out is None:
+            out = torch.empty((N, H, W, prog.n_out), device=x.device, dtype=x.dtype)
+        y, d.Co_total = out, out.shape[3]
+    d.co_off, d.act, d.flags = co_off, act, flags
+    _lib.call("msg_conv_shift", ctypes.byref(d), ops._p(x), ops._p(w_rows), ops._p(bias), ops._p(y), ops._p(stats),
               ops._stream())
     return nchw_out if nchw_out is not None else out

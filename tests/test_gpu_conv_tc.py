@@ -146,3 +146,35 @@ def test_slab_input_conv(c, H, W):
     ref = F.conv2d(x, w, b, padding=3)
     assert_parity(nchw(y), ref, 1e-2, "7x7 input conv")
     assert_parity(st, torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1), 3e-3, "stats")
+
+
+# ---- taps-as-N kernel (csrc/conv_shift.cu) ----------------------------------------------------------
+@pytest.mark.parametrize("H,W", [(16, 128), (8, 256), (12, 72), (6, 512), (5, 120)])
+def test_shift_msb64(H, W):
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(0)
+    N, C, q, dt = 2, 64, 16, torch.bfloat16
+    x = torch.randn(N, C, H, W, device=DEV).to(dt).float()
+    ws = [(torch.randn(q, C, k, k, device=DEV) * (1.0 / (C * k * k) ** 0.5)).to(dt).float() for k in (1, 3, 3, 3)]
+    bs = [torch.randn(q, device=DEV) for _ in range(4)]
+    ref = torch.cat([F.conv2d(x, w, b, padding=(w.shape[2] // 2) * d, dilation=d)
+                     for w, b, d in zip(ws, bs, (1, 1, 2, 4))], 1)
+    prog = slab.msb64_shift_program()
+    st = ops.new_stats(N, C, DEV)
+    y = slab.conv_shift(prog, nhwc(x), slab.msb64_shift_weights(ws), torch.cat(bs).contiguous(), stats=st)
+    assert_parity(nchw(y), ref, 1e-2, "taps-as-N fused branches")
+    assert_parity(st, torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1), 3e-3, "stats")
+
+
+@pytest.mark.parametrize("c,H,W", [(64, 16, 128), (64, 8, 384), (128, 8, 128), (64, 24, 40), (64, 4, 122)])
+def test_shift_output_conv(c, H, W):
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(1)
+    N, dt = 2, torch.bfloat16
+    x = torch.randn(N, c, H, W, device=DEV).to(dt).float()
+    w = (torch.randn(3, c, 7, 7, device=DEV) * 0.02).to(dt).float()
+    b = torch.randn(3, device=DEV)
+    prog = slab.conv7_out_shift_program(c)
+    y = torch.empty(N, 3, H, W, device=DEV)
+    slab.conv_shift(prog, nhwc(x), slab.conv7_out_shift_weights(prog, w), b, act=ops.ACT_TANH, nchw_out=y)
+    assert_parity(y, torch.tanh(F.conv2d(x, w, b, padding=3)), 1e-2, "7x7 output conv + tanh (taps-as-N)")

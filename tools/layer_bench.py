@@ -89,6 +89,17 @@ def main():
         y = torch.empty(N, 3, S, S, device=dev)
         ms = time_fn(lambda: slab.conv_slab(prog, x, wsl, None, act=3, nchw_out=y))
         print(f"{'slab output 7x7 64->3 @S':32s} {ms:8.3f} ms  {2.0 * N * S * S * 3 * c * 49 / ms / 1e9:8.1f} TF/s  {(x.numel() * 2 + y.numel() * 4) / ms / 1e6:8.0f} GB/s")
+        x = torch.randn(N, S, S, c, device=dev).to(dt)
+        prog = slab.conv7_out_shift_program(c)
+        wsl = slab.conv7_out_shift_weights(prog, torch.randn(3, c, 7, 7, device=dev) * 0.02)
+        ms = time_fn(lambda: slab.conv_shift(prog, x, wsl, None, act=3, nchw_out=y))
+        print(f"{'shift output 7x7 64->3 @S':32s} {ms:8.3f} ms  {2.0 * N * S * S * 3 * c * 49 / ms / 1e9:8.1f} TF/s  {(x.numel() * 2 + y.numel() * 4) / ms / 1e6:8.0f} GB/s")
+        prog = slab.msb64_shift_program()
+        wsl = slab.msb64_shift_weights([torch.randn(16, 64, k, k, device=dev) * 0.05 for k in (1, 3, 3, 3)])
+        out = torch.empty(N, S, S, 64, device=dev, dtype=dt)
+        st = ops.new_stats(N, 64, dev)
+        ms = time_fn(lambda: slab.conv_shift(prog, x, wsl, None, out=out, stats=st))
+        print(f"{'shift MSB branches C=64 @S':32s} {ms:8.3f} ms  {2.0 * N * S * S * 16 * 64 * 28 / ms / 1e9:8.1f} TF/s  {2 * x.numel() * 2 / ms / 1e6:8.0f} GB/s")
         x8 = torch.randn(N, S, S, 8, device=dev).to(dt)
         prog = slab.conv7_in_program(c)
         wsl = slab.conv7_in_weight_slab(prog, torch.randn(c, 3, 7, 7, device=dev) * 0.1)
