@@ -251,6 +251,61 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Secondary workload (BASELINE.json configs[3]): EnhancedCycleGAN.train_step, batch 8 per GPU at
+    256x256, bf16, data-parallel (one flat NCCL all-reduce per optimizer per step)."""
+    import torch.distributed as dist
+    from multi_style_transfer_gan_b200 import _lib, profiler
+    from multi_style_transfer_gan_b200.enhanced_train import EnhancedCycleGAN
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)                       # identical init on every rank
+    c = args.channels
+    m = EnhancedCycleGAN(channels=c, num_transformer_blocks=3 if c == 64 else 1, precision=args.precision, device=dev)
+    B, S = args.train_batch, args.train_size
+    A = synth_images(B, S, S, seed=11 + rank).pin_memory()
+    Bm = synth_images(B, S, S, seed=12 + rank).pin_memory()
+    for _ in range(args.warmup):
+        m.train_step(A, Bm)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launches
+    profiler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = m.train_step(A, Bm)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    breakdown = profiler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        line = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": f"EnhancedCycleGAN.train_step (2 G + 2 D, LSGAN + cycle + identity + structure losses, "
+                                       f"fused Adam), c={c}, batch {B} per GPU at {S}x{S}", "global_batch": B * world,
+                           "parallelism": f"data-parallel x{world}, 2 flat NCCL all-reduces per step"},
+                "gpu_launches": _lib.launches - l0, "losses": losses,
+                "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": 2 * A.numel() * 4, "d2h_bytes_per_step": 20},
+                "breakdown_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,13 +318,16 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="stylise", choices=["stylise", "train"])
+    ap.add_argument("--train-batch", type=int, default=8)
+    ap.add_argument("--train-size", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (the msg_b200 path has no CPU fallback); use --impl reference for the CPU arm")
-        run_ours(args)
+        (run_train if args.workload == "train" else run_ours)(args)
 
 
 if __name__ == "__main__":
