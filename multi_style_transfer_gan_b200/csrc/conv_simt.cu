@@ -431,6 +431,11 @@ int conv_validate(const msg_conv_desc* d) { return validate_desc(d); }
 
 }  // namespace msg
 
+namespace msg {
+bool conv2d_wgrad_tc_supported(const msg_conv_desc* d, const void* x, const void* dy);
+int conv2d_wgrad_tc(const msg_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+}  // namespace msg
+
 using namespace msg;
 
 extern "C" int msg_conv2d_wgrad(const msg_conv_desc* d, const void* x, const void* dy,
@@ -438,6 +443,8 @@ extern "C" int msg_conv2d_wgrad(const msg_conv_desc* d, const void* x, const voi
   int rc = validate_desc(d);
   if (rc) return rc;
   MSG_REQUIRE(!(d->flags & MSG_CONV_OUT_NCHW_F32), MSG_ERR_UNSUPPORTED, "wgrad: NCHW dy unsupported");
+  if (!(d->flags & MSG_CONV_FORCE_SIMT) && conv2d_wgrad_tc_supported(d, x, dy))
+    return conv2d_wgrad_tc(d, x, dy, dw_packed, as_stream(stream));      // tcgen05 kernel (conv_wgrad_tc.cu)
   const int K = d->KH * d->KW * d->Cin;
   const long long M = (long long)d->N * d->Hg * d->Wg;
   unsigned gx = (K + 63) / 64, gy = (d->Cout + 63) / 64;

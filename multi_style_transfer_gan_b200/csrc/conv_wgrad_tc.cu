@@ -1,0 +1,330 @@
+// tcgen05 weight-gradient kernel (sm_100a, bf16 operands, fp32 accumulate).
+//
+//   dw[co][tap][ci] += sum over output pixels p of  dy[p][co] * x[p @ tap][ci]
+// is a GEMM whose CONTRACTION dimension is the pixel index: both operands are "MN-major" (channels
+// contiguous, pixels along K).  That is exactly how a TMA box of the NHWC tensors lands in shared
+// memory -- rows = pixels, 128 B = 64 channels, 128B swizzle -- so no transposition is needed:
+//   A = dy tile  [128 pixels x 128 co]  (two 64-channel boxes, LBO = 16 KB apart)
+//   B = x tiles  [128 pixels x 64 ci] for up to FOUR (tap, ci-block) pairs, 16 KB apart = N up to 256
+// and one k-block (128 pixels) is 8 x tcgen05.mma (M=128, N=256, K=16) with a_major = b_major = MN.
+// The x tile of a tap is the same shifted / strided TMA box the forward kernel uses (zero fill =
+// padding).  A CTA owns one (co tile, group of <=4 pairs) and a contiguous range of pixel tiles; the
+// fp32 accumulator stays in TMEM for the whole range and is added to dw (packed [Cout][tap][Cin] fp32)
+// with atomics at the end.  Channels beyond Cout are TMA out-of-bounds = zero rows.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace msg {
+namespace {
+
+constexpr int BM = 128;           // pixels per k-block
+constexpr int TILE = BM * 128;    // one [128 px x 64 ch] box
+constexpr int NTHREADS = 192;
+constexpr int MAXP = 4;           // (tap, ci-block) pairs per CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// MN-major, 128-byte swizzle: atoms of [8 K-rows x 64 MN-elements] = 1024 B; SBO = 1024 (next 8 K rows),
+// LBO = distance to the next 64-element MN block (here: the next 16 KB box).
+__device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct WgParams {
+  msg_conv_desc d;
+  float* dw;
+  int Wt, R;             // pixel tile = R rows x Wt pixels of the GEMM grid
+  int m_tiles;           // pixel tiles in total
+  int cblocks;           // Cin / 64
+  int n_pairs;           // KH*KW*cblocks
+  int groups;            // ceil(n_pairs / MAXP)
+  int co_tiles;          // ceil(Cout / 128)
+  int splits;            // pixel-range splits
+  int stages;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                     const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const msg_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  // work item of this CTA
+  int w = blockIdx.x;
+  const int split = w % p.splits; w /= p.splits;
+  const int grp = w % p.groups;
+  const int cot = w / p.groups;
+  const int pair0 = grp * MAXP;
+  const int npair = (p.n_pairs - pair0) < MAXP ? (p.n_pairs - pair0) : MAXP;
+  const int mt_begin = (int)((long long)split * p.m_tiles / p.splits);
+  const int mt_end = (int)((long long)(split + 1) * p.m_tiles / p.splits);
+  const int stage_bytes = (2 + MAXP) * TILE;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sBar = base + S * stage_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * stage_bytes + 8 * (2 * S + 1));
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
+  const uint32_t done_bar = sBar + 8u * (2 * S);
+  const uint32_t ncols = (uint32_t)(npair * 64);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < ncols) tmem_cols <<= 1;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      mbar_init(done_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapDY)) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_row = d.Wg / p.Wt;
+  const int tile_rows = d.Hg / p.R;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int mt = mt_begin; mt < mt_end; ++mt, ++it) {
+        const int img = mt / (tile_rows * tiles_per_row);
+        const int rem = mt - img * (tile_rows * tiles_per_row);
+        const int rg = rem / tiles_per_row, cg = rem - rg * tiles_per_row;
+        const int i0 = rg * p.R, j0 = cg * p.Wt;
+        const int s = it % S;
+        if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+        const uint32_t st = base + s * stage_bytes;
+        mbar_expect_tx(full_bar(s), (uint32_t)((2 + npair) * TILE));
+        // dy: two 64-channel boxes of this co tile (channels >= Cout are out of bounds -> zeros)
+        const int oy = i0 * d.out_stride + d.out_off_h, ox = j0 * d.out_stride + d.out_off_w;
+        tma_load_4d(st, &mapDY, full_bar(s), cot * 128, ox, oy, img);
+        tma_load_4d(st + TILE, &mapDY, full_bar(s), cot * 128 + 64, ox, oy, img);
+        // x: one shifted / strided box per (tap, ci-block) pair
+        const int w_base = j0 * d.in_stride - d.pad_w, h_base = i0 * d.in_stride - d.pad_h;
+        for (int pi = 0; pi < npair; ++pi) {
+          const int pr = pair0 + pi;
+          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
+          const int th = tap / d.KW, tw = tap - th * d.KW;
+          tma_load_4d(st + (2 + pi) * TILE, &mapX, full_bar(s), cb * 64, w_base + tw * d.dil, h_base + th * d.dil, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    // D[co][pair*64 + ci] += A^T B ; both operands MN-major (bits 15, 16), M = 128, N = npair*64
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t it = 0;
+    for (int mt = mt_begin; mt < mt_end; ++mt, ++it) {
+      const int s = it % S;
+      mbar_wait(full_bar(s), (it / S) & 1);
+      tc_fence_after();
+      const uint32_t st = base + s * stage_bytes;
+      const uint64_t da = make_mn_sw128_desc(st, TILE);
+      const uint64_t db = make_mn_sw128_desc(st + 2 * TILE, TILE);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks)       // 16 pixels per MMA = 2 swizzle atoms = 2048 B further down
+          umma_bf16(tmem_base, da + (uint64_t)(ks * 128), db + (uint64_t)(ks * 128), idesc, (it | ks) != 0);
+      }
+      __syncwarp();
+      if (elect_one()) umma_commit(empty_bar(s));
+    }
+    __syncwarp();
+    if (elect_one()) umma_commit(done_bar);
+  } else {
+    // ===================================== epilogue: TMEM -> fp32 atomics on dw =====================
+    const int q = warp & 3;
+    const int co = cot * 128 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int Ktot = d.KH * d.KW * d.Cin;
+    if (mt_end > mt_begin) {
+      for (int pi = 0; pi < npair; ++pi) {
+        const int pr = pair0 + pi;
+        const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
+        float* dst = p.dw + (size_t)co * Ktot + (size_t)tap * d.Cin + cb * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          __syncwarp();
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + h * 32), v);
+          if (co < d.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool pick_tiling(const msg_conv_desc* d, int* Wt, int* R) {
+  if (d->Wg >= 128) {
+    if (d->Wg % 128) return false;
+    *Wt = 128; *R = 1;
+    return true;
+  }
+  if (128 % d->Wg) return false;
+  *Wt = d->Wg; *R = 128 / d->Wg;
+  return d->Hg % *R == 0;
+}
+
+}  // namespace
+
+bool conv2d_wgrad_tc_supported(const msg_conv_desc* d, const void* x, const void* dy) {
+  if (d->dtype != MSG_BF16) return false;
+  if (d->flags & (MSG_CONV_IN_NORM | MSG_CONV_OUT_NCHW_F32)) return false;
+  if (d->Cin % 64 || (d->Ci_total & 7) || (d->ci_off & 7)) return false;
+  if ((d->Co_total & 7) || (d->co_off & 7)) return false;
+  if (((uintptr_t)x | (uintptr_t)dy) & 15) return false;
+  if ((d->in_stride != 1 && d->in_stride != 2) || (d->out_stride != 1 && d->out_stride != 2)) return false;
+  int Wt, R;
+  if (!pick_tiling(d, &Wt, &R)) return false;
+  if (Wt * d->in_stride > 256 || R * d->in_stride > 256 || Wt * d->out_stride > 256 || R * d->out_stride > 256) return false;
+  return get_encode() != nullptr;
+}
+
+int conv2d_wgrad_tc(const msg_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled unavailable");
+  WgParams p;
+  p.d = *d; p.dw = dw;
+  MSG_REQUIRE(pick_tiling(d, &p.Wt, &p.R), MSG_ERR_UNSUPPORTED, "wgrad_tc: unsupported plane geometry");
+  p.m_tiles = (int)((long long)d->N * d->Hg * d->Wg / BM);
+  p.cblocks = d->Cin / 64;
+  p.n_pairs = d->KH * d->KW * p.cblocks;
+  p.groups = (p.n_pairs + MAXP - 1) / MAXP;
+  p.co_tiles = (d->Cout + 127) / 128;
+  const int items = p.groups * p.co_tiles;
+  int splits = (2 * sm_count() + items - 1) / items;     // ~2 CTAs' worth of work items per SM in total
+  if (splits > p.m_tiles) splits = p.m_tiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.stages = 2;
+  const size_t smem = (size_t)p.stages * (2 + MAXP) * TILE + 8 * (2 * p.stages + 1) + 16 + 1024;
+
+  CUtensorMap mapX, mapDY;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->Wi * d->Ci_total * 2,
+                             (cuuint64_t)d->Hi * d->Wi * d->Ci_total * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * d->in_stride), (cuuint32_t)(p.R * d->in_stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->in_stride, (cuuint32_t)d->in_stride, 1};
+    void* base = (void*)((const __nv_bfloat16*)x + d->ci_off);
+    CUresult r = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->Co_total * 2, (cuuint64_t)d->Wo * d->Co_total * 2,
+                             (cuuint64_t)d->Ho * d->Wo * d->Co_total * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * d->out_stride), (cuuint32_t)(p.R * d->out_stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->out_stride, (cuuint32_t)d->out_stride, 1};
+    void* base = (void*)((const __nv_bfloat16*)dy + d->co_off);
+    CUresult r = enc(&mapDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = p.co_tiles * p.groups * p.splits;
+  conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapX, mapDY, p);
+  return check_launch("conv_wgrad_tc_kernel");
+}
+
+}  // namespace msg

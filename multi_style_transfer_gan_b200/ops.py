@@ -165,7 +165,7 @@ class ConvGeom:
             conv_raw(d, dy, wpd, None, out)
         return out
 
-    def wgrad(self, x, dy, dw, db=None, dy_c_off=0, ci_off=0):
+    def wgrad(self, x, dy, dw, db=None, dy_c_off=0, ci_off=0, extra_flags=0):
         """Accumulates into dw (fp32, PyTorch weight layout) and db (fp32 [Cout])."""
         _dev(x)
         N, Hi, Wi, Ci_total = x.shape
@@ -174,7 +174,7 @@ class ConvGeom:
         dwp = torch.zeros(dw.numel(), device=x.device, dtype=torch.float32)
         if self.kind == "conv":
             d = make_desc(dt, N, Hi, Wi, Ci_total, ci_off, self.Cin, Ho, Wo, Cdy, dy_c_off, self.Cout, Ho, Wo,
-                          self.k, self.k, self.stride, self.pad, self.pad, self.dil)
+                          self.k, self.k, self.stride, self.pad, self.pad, self.dil, flags=extra_flags)
             _lib.call("msg_conv2d_wgrad", ctypes.byref(d), _p(x), _p(dy), _p(dwp), _stream())
             unpack_wgrad(dwp, dw.shape, PACK_FWD, dw)
         else:
@@ -182,7 +182,7 @@ class ConvGeom:
             for ph in range(2):
                 for pw in range(2):
                     d = make_desc(dt, N, Hi, Wi, Ci_total, ci_off, self.Cin, Ho, Wo, Cdy, dy_c_off, self.Cout,
-                                  Hi, Wi, 2, 2, 1, 1 - ph, 1 - pw, 1, 2, ph, pw)
+                                  Hi, Wi, 2, 2, 1, 1 - ph, 1 - pw, 1, 2, ph, pw, flags=extra_flags)
                     _lib.call("msg_conv2d_wgrad", ctypes.byref(d), _p(x), _p(dy),
                               _p(dwp[(ph * 2 + pw) * per_phase:]), _stream())
             unpack_wgrad(dwp, dw.shape, PACK_CONVT_PHASES, dw)

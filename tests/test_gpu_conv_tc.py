@@ -178,3 +178,39 @@ def test_shift_output_conv(c, H, W):
     y = torch.empty(N, 3, H, W, device=DEV)
     slab.conv_shift(prog, nhwc(x), slab.conv7_out_shift_weights(prog, w), b, act=ops.ACT_TANH, nchw_out=y)
     assert_parity(y, torch.tanh(F.conv2d(x, w, b, padding=3)), 1e-2, "7x7 output conv + tanh (taps-as-N)")
+
+
+# ---- tcgen05 wgrad (csrc/conv_wgrad_tc.cu) -----------------------------------------------------------
+WGRAD_CASES = [
+    ("conv", 64, 128, 4, 2, 1, 1, 64, 64),     # down1.0
+    ("conv", 128, 256, 4, 2, 1, 1, 32, 32),    # down2.0
+    ("conv", 128, 384, 1, 1, 0, 1, 32, 32),    # qkv
+    ("conv", 64, 64, 1, 1, 0, 1, 32, 128),     # proj / fusion at C=64
+    ("conv", 128, 32, 3, 1, 2, 2, 32, 32),     # branch (N small: padded to M=128 by TMA zero fill)
+    ("conv", 64, 16, 3, 1, 4, 4, 16, 128),     # branch4 at C=64
+    ("convT", 256, 128, 4, 2, 1, 1, 16, 16),   # up1.0
+    ("convT", 128, 64, 4, 2, 1, 1, 32, 32),    # up2.0
+    ("conv", 64, 8, 7, 1, 3, 1, 32, 64),       # output conv (padded filters)
+    ("conv", 512, 512, 3, 1, 1, 1, 16, 16),    # D structure head
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_wgrad_tc_vs_simt_and_torch(case):
+    from multi_style_transfer_gan_b200 import ops
+    kind, Cin, Cout, k, s, p, d, H, W = case
+    torch.manual_seed(0)
+    g = ops.ConvGeom(kind, Cin, Cout, k, s, p, d)
+    N, dt = 2, torch.bfloat16
+    x = torch.randn(N, Cin, H, W, device=DEV).to(dt).float()
+    w = torch.zeros(*g.weight_shape(), device=DEV, requires_grad=True)
+    out = F.conv_transpose2d(x, w, None, stride=2, padding=1) if kind == "convT" else F.conv2d(x, w, None, stride=s, padding=p, dilation=d)
+    dy = torch.randn_like(out).to(dt).float()
+    out.backward(dy)
+    dw_tc = torch.zeros_like(w)
+    g.wgrad(nhwc(x), nhwc(dy), dw_tc)
+    dw_si = torch.zeros_like(w)
+    g.wgrad(nhwc(x), nhwc(dy), dw_si, extra_flags=ops.CONV_FORCE_SIMT)
+    assert_parity(dw_si, w.grad, 1e-2, "simt wgrad vs torch")
+    assert_parity(dw_tc, w.grad, 1e-2, "tcgen05 wgrad vs torch")
+    assert_parity(dw_tc, dw_si, 2e-3, "tcgen05 wgrad vs simt")
