@@ -44,6 +44,12 @@ __device__ __forceinline__ void cpa16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
 template <int C>
 __global__ void __launch_bounds__(LT_THREADS, (C == 64 ? 8 : C == 128 ? 4 : 3))
 local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, int W,
@@ -108,26 +114,40 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
     //      scaled by both norms: half the smem writes.  8 threads per pixel.
     {
       const int p = tid >> 3, part = tid & 7;
-      constexpr int EPT = C / 8;              // elements per thread
-      const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(qs + p * PITCH) + part * (EPT / 2);
-      __nv_bfloat162* kp = reinterpret_cast<__nv_bfloat162*>(ks + p * PITCH) + part * (EPT / 2);
-      float2 kv[EPT / 2];
+      constexpr int VPT = C / 64;             // 16-byte vectors per thread; vector v covers chunk part + 8 v, so a
+                                              // quarter-warp touches 128 contiguous bytes (conflict-free LDS/STS.128)
+      const uint4* qp = reinterpret_cast<const uint4*>(qs + p * PITCH) + part;
+      uint4* kp = reinterpret_cast<uint4*>(ks + p * PITCH) + part;
+      uint4 kv[VPT];
       float sq = 0.f, sk = 0.f;
 #pragma unroll
-      for (int e = 0; e < EPT / 2; ++e) {
-        const float2 qv = __bfloat1622float2(qp[e]);
-        kv[e] = __bfloat1622float2(kp[e]);
-        sq = fmaf(qv.x, qv.x, fmaf(qv.y, qv.y, sq));
-        sk = fmaf(kv[e].x, kv[e].x, fmaf(kv[e].y, kv[e].y, sk));
+      for (int v = 0; v < VPT; ++v) {
+        const uint4 qv = qp[8 * v];
+        kv[v] = kp[8 * v];
+        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv[v].x, kv[v].y, kv[v].z, kv[v].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float q0 = __uint_as_float(qw[e] << 16), q1 = __uint_as_float(qw[e] & 0xffff0000u);
+          const float k0 = __uint_as_float(kw[e] << 16), k1 = __uint_as_float(kw[e] & 0xffff0000u);
+          sq = fmaf(q0, q0, fmaf(q1, q1, sq));
+          sk = fmaf(k0, k0, fmaf(k1, k1, sk));
+        }
       }
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
         sk += __shfl_xor_sync(0xffffffffu, sk, o);
       }
-      const float sc = 1.f / (fmaxf(sqrtf(sq), 1e-12f) * fmaxf(sqrtf(sk), 1e-12f));
+      // 1/(|q||k|) with the reference's eps clamp on each norm; log2(e) folded in so exp becomes ex2
+      const float sc = 1.4426950408889634f * rsqrtf(fmaxf(sq, 1e-24f)) * rsqrtf(fmaxf(sk, 1e-24f));
 #pragma unroll
-      for (int e = 0; e < EPT / 2; ++e) kp[e] = __floats2bfloat162_rn(kv[e].x * sc, kv[e].y * sc);
+      for (int v = 0; v < VPT; ++v) {
+        uint32_t kw[4] = {kv[v].x, kv[v].y, kv[v].z, kv[v].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          kw[e] = pack_bf16x2(__uint_as_float(kw[e] << 16) * sc, __uint_as_float(kw[e] & 0xffff0000u) * sc);
+        kp[8 * v] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+      }
     }
     __syncthreads();
     // ---- attention rows: each warp takes 16-row slabs of S
@@ -150,39 +170,36 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
         mma_bf16(acc[nt], afr, bfr[0], bfr[1]);
         mma_bf16(acc[nt + 1], afr, bfr[2], bfr[3]);
       }
-      float rs0 = 0.f, rs1 = 0.f;
+      // P = exp(S) straight into packed bf16 pairs (K carries log2(e), so this is one packed ex2 per
+      // pair).  The S accumulator layout (row g | g+8, cols 2q4, 2q4+1) is the B-fragment layout of P^T,
+      // so the second GEMM is computed transposed: O^T[pixel][i] = sum_j V^T[pixel][j] P^T[j][i], which
+      // puts channel pairs in one thread (4-byte conflict-free stores into the [pixel][channel] tile),
+      // and an all-ones A operand yields the softmax row sums in the same column layout for free.
+      uint32_t pk[C / 8][2];
 #pragma unroll
       for (int nt = 0; nt < C / 8; ++nt) {
-        acc[nt][0] = __expf(acc[nt][0]); acc[nt][1] = __expf(acc[nt][1]);
-        acc[nt][2] = __expf(acc[nt][2]); acc[nt][3] = __expf(acc[nt][3]);
-        rs0 += acc[nt][0] + acc[nt][1];
-        rs1 += acc[nt][2] + acc[nt][3];
+        pk[nt][0] = ex2_bf16x2(pack_bf16x2(acc[nt][0], acc[nt][1]));
+        pk[nt][1] = ex2_bf16x2(pack_bf16x2(acc[nt][2], acc[nt][3]));
       }
-      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
-      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float rsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
 #pragma unroll
       for (int ks16 = 0; ks16 < C / 16; ++ks16) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(acc[2 * ks16][0], acc[2 * ks16][1]);
-        pa[1] = pack_bf16x2(acc[2 * ks16][2], acc[2 * ks16][3]);
-        pa[2] = pack_bf16x2(acc[2 * ks16 + 1][0], acc[2 * ks16 + 1][1]);
-        pa[3] = pack_bf16x2(acc[2 * ks16 + 1][2], acc[2 * ks16 + 1][3]);
-        uint32_t vb[4];
-        // B = V stored [pixel][channel] = [n][k]: (p 0-7, j 16ks..), (p 0-7, j 16ks+8..), (p 8-15, ..), (p 8-15, ..+8)
-        ldsm_x4(vs_a + (r8 + 8 * (mi >> 1)) * PITCH + (16 * ks16 + 8 * (mi & 1)) * 2, vb);
-        mma_bf16(o[0], pa, vb[0], vb[1]);
-        mma_bf16(o[1], pa, vb[2], vb[3]);
+        uint32_t va[4];
+        // A = V^T stored [pixel][channel] = [m][k]: (p 0-7, j 16ks..), (p 8-15, j 16ks..), (p 0-7, +8), (p 8-15, +8)
+        ldsm_x4(vs_a + (r8 + 8 * (mi & 1)) * PITCH + (16 * ks16 + 8 * (mi >> 1)) * 2, va);
+        mma_bf16(o[0], va, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
+        mma_bf16(o[1], va, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
+        mma_bf16(rsum[0], ones, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
+        mma_bf16(rsum[1], ones, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
       }
-      const float inv0 = 1.f / rs0, inv1 = 1.f / rs1;
-      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(os);
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const int p0 = 8 * nt + 2 * q4;
-        ob[(p0) * (PITCH / 2) + i0 + g] = __float2bfloat16_rn(o[nt][0] * inv0);
-        ob[(p0 + 1) * (PITCH / 2) + i0 + g] = __float2bfloat16_rn(o[nt][1] * inv0);
-        ob[(p0) * (PITCH / 2) + i0 + g + 8] = __float2bfloat16_rn(o[nt][2] * inv1);
-        ob[(p0 + 1) * (PITCH / 2) + i0 + g + 8] = __float2bfloat16_rn(o[nt][3] * inv1);
+        const float inv0 = __fdividef(1.f, rsum[nt][0]), inv1 = __fdividef(1.f, rsum[nt][1]);   // sums are in [C/e, C e]
+        const int col = (i0 + 8 * nt + 2 * q4) * 2;
+        *reinterpret_cast<uint32_t*>(os + g * PITCH + col) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv1);
+        *reinterpret_cast<uint32_t*>(os + (g + 8) * PITCH + col) = pack_bf16x2(o[nt][2] * inv0, o[nt][3] * inv1);
       }
     }
     __syncthreads();
