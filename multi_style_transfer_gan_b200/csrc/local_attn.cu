@@ -225,6 +225,8 @@ local_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, int
 namespace msg {
 bool local_attn_tc_supported(int dtype, int C, const void* qkv, const void* out);
 int local_attn_fwd_tc(const void* qkv, int N, int H, int W, int C, void* out, cudaStream_t st);
+bool local_attn_bwd_tc_supported(int dtype, int C, const void* qkv, const void* dout, const void* dqkv);
+int local_attn_bwd_tc(const void* qkv, const void* dout, int N, int H, int W, int C, void* dqkv, cudaStream_t st);
 }  // namespace msg
 
 using namespace msg;
@@ -260,6 +262,8 @@ extern "C" int msg_local_attn_bwd(int dtype, const void* qkv, const void* dout, 
                                   int C, int ws, void* dqkv, void* stream) {
   MSG_REQUIRE(ws == 4, MSG_ERR_UNSUPPORTED, "local_attn: only window_size=4");
   MSG_REQUIRE(N > 0 && C > 0 && H % 4 == 0 && W % 4 == 0, MSG_ERR_SHAPE, "local_attn_bwd: bad shape");
+  if (local_attn_bwd_tc_supported(dtype, C, qkv, dout, dqkv))
+    return local_attn_bwd_tc(qkv, dout, N, H, W, C, dqkv, as_stream(stream));
   size_t smem = (size_t)(7 * P * C + 2 * C + 4 * P) * sizeof(float) + 2 * P * sizeof(int);
   MSG_REQUIRE(smem <= 227 * 1024, MSG_ERR_UNSUPPORTED, "local_attn_bwd: C=%d too large", C);
   long long nwin = (long long)N * (H / 4) * (W / 4);

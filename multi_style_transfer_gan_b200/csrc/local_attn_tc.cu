@@ -13,42 +13,15 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "la_mma.cuh"
 
 namespace msg {
 namespace {
+using namespace la;
 
 constexpr int LT_THREADS = 128;
 constexpr int LT_WARPS = 4;
 constexpr int P16 = 16;
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ void cpa16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
 
 template <int C>
 __global__ void __launch_bounds__(LT_THREADS, (C == 64 ? 8 : C == 128 ? 4 : 3))
@@ -114,23 +87,22 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
     //      scaled by both norms: half the smem writes.  8 threads per pixel.
     {
       const int p = tid >> 3, part = tid & 7;
-      constexpr int VPT = C / 64;             // 16-byte vectors per thread; vector v covers chunk part + 8 v, so a
+      constexpr int VPT = (C + 63) / 64;      // 16-byte vectors per thread; vector v covers chunk part + 8 v, so a
                                               // quarter-warp touches 128 contiguous bytes (conflict-free LDS/STS.128)
+      const bool act = part * 8 < C;          // C = 32: only 4 chunks per pixel
       const uint4* qp = reinterpret_cast<const uint4*>(qs + p * PITCH) + part;
       uint4* kp = reinterpret_cast<uint4*>(ks + p * PITCH) + part;
       uint4 kv[VPT];
       float sq = 0.f, sk = 0.f;
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
-        const uint4 qv = qp[8 * v];
-        kv[v] = kp[8 * v];
+        const uint4 qv = act ? qp[8 * v] : make_uint4(0, 0, 0, 0);
+        kv[v] = act ? kp[8 * v] : make_uint4(0, 0, 0, 0);
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv[v].x, kv[v].y, kv[v].z, kv[v].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float q0 = __uint_as_float(qw[e] << 16), q1 = __uint_as_float(qw[e] & 0xffff0000u);
-          const float k0 = __uint_as_float(kw[e] << 16), k1 = __uint_as_float(kw[e] & 0xffff0000u);
-          sq = fmaf(q0, q0, fmaf(q1, q1, sq));
-          sk = fmaf(k0, k0, fmaf(k1, k1, sk));
+          sq = fmaf(bf_lo(qw[e]), bf_lo(qw[e]), fmaf(bf_hi(qw[e]), bf_hi(qw[e]), sq));
+          sk = fmaf(bf_lo(kw[e]), bf_lo(kw[e]), fmaf(bf_hi(kw[e]), bf_hi(kw[e]), sk));
         }
       }
 #pragma unroll
@@ -144,9 +116,8 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
       for (int v = 0; v < VPT; ++v) {
         uint32_t kw[4] = {kv[v].x, kv[v].y, kv[v].z, kv[v].w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          kw[e] = pack_bf16x2(__uint_as_float(kw[e] << 16) * sc, __uint_as_float(kw[e] & 0xffff0000u) * sc);
-        kp[8 * v] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+        for (int e = 0; e < 4; ++e) kw[e] = pack_bf16x2(bf_lo(kw[e]) * sc, bf_hi(kw[e]) * sc);
+        if (act) kp[8 * v] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
       }
     }
     __syncthreads();

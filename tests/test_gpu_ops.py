@@ -158,7 +158,7 @@ def test_instnorm_blended_affine():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("C,H,W", [(8, 8, 8), (32, 16, 24), (128, 8, 8), (256, 8, 4)])
+@pytest.mark.parametrize("C,H,W", [(8, 8, 8), (32, 16, 24), (64, 12, 8), (128, 8, 8), (256, 8, 4)])
 def test_local_attention_core(dtype, C, H, W):
     from multi_style_transfer_gan_b200 import ops
     torch.manual_seed(4)

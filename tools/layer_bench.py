@@ -126,6 +126,9 @@ def main():
             ms = time_fn(lambda: ops.local_attn_fwd(qkv))
             fl = 2.0 * 2 * N * (H // 4) ** 2 * C * C * 16
             print(f"{'local_attn C=%d @%d' % (C, H):32s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TF/s  {qkv.numel() * 2 * 4 / 3 / ms / 1e6:8.0f} GB/s")
+            dy = torch.randn(N, H, H, C, device=dev).to(dt)
+            ms = time_fn(lambda: ops.local_attn_bwd(qkv, dy))
+            print(f"{'local_attn bwd C=%d @%d' % (C, H):32s} {ms:8.3f} ms  {'':8s}       {qkv.numel() * 2 * 7 / 3 / ms / 1e6:8.0f} GB/s")
 
 
 if __name__ == "__main__":
