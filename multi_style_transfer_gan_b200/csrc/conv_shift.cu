@@ -155,16 +155,18 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (lane == 0) {
       mbar_expect_tx(wres_bar, (uint32_t)p.b_bytes);          // weights: once, boxes of 32 rows
       for (int r = 0; r < p.b_rows; r += 32) tma_load_2d(sB + r * 128, &mapB, wres_bar, 0, r);
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      bool wrapped = false;
       for (int t = t_begin; t < t_end; ++t) {
         const int seg = t % p.segs, ny = t / p.segs;
         const int yrow = ny % d.H, img = ny / d.H;
         const int x0 = seg * p.Wv - d.halo;
-        for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
-          const int s = it % S;
-          if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+        for (int kb = 0; kb < d.n_kblocks; ++kb) {
+          if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), A_BYTES);
           tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), d.kb_cb[kb] * 64, x0, yrow + d.kb_dy[kb], img);
+          if (++s == S) { s = 0; ph ^= 1u; wrapped = true; }   // no div/mod by the runtime stage count
         }
       }
     }
@@ -172,33 +174,45 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ===================================== MMA issuer (warp-uniform, elected lane issues) =============
     const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
     const uint64_t sw128_hi = make_sw128_desc(0);
-    uint32_t it = 0, lt = 0;
+    // Single-warp serial issue: every instruction per K block is on the critical path.  Lane kb keeps the
+    // tile-invariant operands of K block kb (<= 32 K blocks) in registers; the loop broadcasts them with
+    // independent shuffles; stage / phase are counted incrementally (no div/mod by the runtime stage count).
+    uint32_t kb_b = 0, kb_idesc = 0, kb_col = 0, kb_acc = 1;
+    if (lane < d.n_kblocks) {
+      kb_b = (sB + (uint32_t)d.kb_wrow[lane] * 128u) >> 4;
+      kb_idesc = idesc0 | ((uint32_t)(d.kb_ncols[lane] >> 3) << 17);
+      kb_col = (uint32_t)d.kb_col0[lane];
+      kb_acc = !d.kb_first[lane];
+    }
+    const uint32_t a_base = sA >> 4;
+    int s = 0;
+    uint32_t ph = 0, lt = 0;
     mbar_wait(wres_bar, 0);
     for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int buf = lt & 1;
       if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot);
-      for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);
+      for (int kb = 0; kb < d.n_kblocks; ++kb) {
+        const uint64_t db = sw128_hi | (uint64_t)__shfl_sync(0xffffffffu, kb_b, kb);
+        const uint32_t idesc = __shfl_sync(0xffffffffu, kb_idesc, kb);
+        const uint32_t dcol = tacc + __shfl_sync(0xffffffffu, kb_col, kb);
+        const uint32_t acc = __shfl_sync(0xffffffffu, kb_acc, kb);
+        const uint64_t da = sw128_hi | (uint64_t)(a_base + (uint32_t)s * (A_BYTES >> 4));
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint64_t da = sw128_hi | (uint64_t)((sA + s * A_BYTES) >> 4);
-        const uint64_t db = sw128_hi | (uint64_t)((sB + (uint32_t)d.kb_wrow[kb] * 128u) >> 4);
-        const uint32_t idesc = idesc0 | ((uint32_t)(d.kb_ncols[kb] >> 3) << 17);
-        const uint32_t dcol = tacc + (uint32_t)d.kb_col0[kb];
-        const uint32_t first = (uint32_t)d.kb_first[kb];
         if (elect_one()) {
-          umma_bf16(dcol, da, db, idesc, !first);
+          umma_bf16(dcol, da, db, idesc, acc);
           umma_bf16(dcol, da + 2, db + 2, idesc, 1);
           umma_bf16(dcol, da + 4, db + 4, idesc, 1);
           umma_bf16(dcol, da + 6, db + 6, idesc, 1);
+          umma_commit(empty_bar(s));
         }
         __syncwarp();
-        if (elect_one()) umma_commit(empty_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
       if (elect_one()) umma_commit(tfull_bar(buf));
+      __syncwarp();
     }
   } else {
     // ===================================== epilogue (warps 2-5) =====================================

@@ -199,14 +199,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int bx = 0; bx * p.b_box_taps < tiles_total; ++bx)
           tma_load_2d(sB + bx * p.b_box_taps * tap_bytes, &mapB, wres_bar, 0, bx * p.b_box_taps * d.ncols);
       }
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      bool wrapped = false;
       for (int t = t_begin; t < t_end; ++t) {
         const int seg = t % p.segs, ny = t / p.segs;
         const int yrow = ny % d.H, img = ny / d.H;
         const int x0 = seg * BM - d.halo;
-        for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
-          const int s = it % S;
-          if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+        for (int kb = 0; kb < d.n_kblocks; ++kb) {
+          if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
           const int t0 = d.kb_tap_begin[kb], t1 = d.kb_tap_begin[kb + 1];
           const int nbox = p.b_resident ? 0 : (d.pixel_pair_k ? 1 : (t1 - t0 + p.b_box_taps - 1) / p.b_box_taps);
           mbar_expect_tx(full_bar(s), p.a_bytes + nbox * p.b_box_taps * tap_bytes);
@@ -224,6 +225,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int bx = 0; bx < nbox; ++bx)
             tma_load_2d(sB + s * p.b_bytes + bx * p.b_box_taps * tap_bytes, &mapB, full_bar(s), 0,
                         row0 + bx * p.b_box_taps * d.ncols);
+          if (++s == S) { s = 0; ph ^= 1u; wrapped = true; }   // no div/mod by the runtime stage count
         }
       }
     }
@@ -239,16 +241,36 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t ch1 = nch > 1 ? (uint32_t)d.Ntot : 0u;
     const uint32_t ch2 = nch > 2 ? (uint32_t)(2 * d.Ntot) : 0u;
     const uint32_t ch3 = nch > 2 ? (uint32_t)(3 * d.Ntot) : ch1;
-    uint32_t it = 0, lt = 0;
+    // pixel-pair mode: lane l <-> tap l (n_taps <= 32, checked on the host); all in 16-byte descriptor units
+    const uint64_t noswz_hi = make_noswz_desc(0, 16u);
+    uint32_t pp_a = 0, pp_b = 0, pp_col = 0, pp_acc = 1;
+    if (d.pixel_pair_k && lane < d.n_taps) {
+      pp_a = (uint32_t)d.tap_sx[lane] >> 4;
+      pp_b = (uint32_t)d.tap_kstep[lane] >> 4;
+      const int chain = nch > 1 ? lane % nch : 0;           // K block 0 starts at tap 0
+      pp_col = (uint32_t)d.tap_acc_col[lane] + (uint32_t)(chain * d.Ntot);
+      pp_acc = !(lane < nch);                                // the first tap of each chain overwrites
+    }
+    // swizzled-slab mode: tile-invariant tap operands {A offset, B offset, TMEM column, overwrite} in 16-byte
+    // descriptor units, one 16-byte smem entry per tap, so the elected lane's issue loop is one LDS.128 + three
+    // adds per tap instead of a chain of indexed constant loads
+    uint4* tap_tab = reinterpret_cast<uint4*>(gen + (sBar + 256u - base));
+    if (p.a_mode != 0) {
+      for (int tp = lane; tp < d.n_taps; tp += 32)
+        tap_tab[tp] = make_uint4((uint32_t)d.tap_sx[tp] >> 4, (uint32_t)d.tap_kstep[tp] >> 4, (uint32_t)d.tap_acc_col[tp],
+                                 (uint32_t)d.tap_first[tp]);
+      __syncwarp();
+    }
+    int s = 0;
+    uint32_t ph = 0, lt = 0;
     if (p.b_resident) mbar_wait(wres_bar, 0);
     for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int buf = lt & 1;
       if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains);
-      for (int kb = 0; kb < d.n_kblocks; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);
+      for (int kb = 0; kb < d.n_kblocks; ++kb) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t a0 = sA + s * p.a_bytes;
         const uint32_t b0 = p.b_resident ? sB : sB + s * p.b_bytes;
@@ -256,25 +278,42 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (p.a_mode != 0) {
           // [pixel][128 B] slab, 128B swizzle: tap shift = +128 B per pixel on the start address; the
           // swizzle is a function of the absolute smem address, so base_offset stays 0 (verified on B200)
-          for (int tp = t0; tp < t1; ++tp) {
-            const uint64_t da = sw128_hi | (uint64_t)((a0 + (uint32_t)d.tap_sx[tp]) >> 4);     // tap_sx: byte offset (host)
-            const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);  // tap_kstep: byte offset
-            const uint32_t dcol = tacc + (uint32_t)d.tap_acc_col[tp];
-            const uint32_t first = (uint32_t)d.tap_first[tp];
-            if (elect_one()) {
-              umma_bf16(dcol, da, db, idesc, !first);
-              umma_bf16(dcol + ch1, da + 2, db + 2, idesc, !(first && nch > 1));
-              umma_bf16(dcol + ch2, da + 4, db + 4, idesc, !(first && nch > 2));
-              umma_bf16(dcol + ch3, da + 6, db + 6, idesc, !(first && nch > 2));
+          const uint32_t a0s = a0 >> 4, b0s = b0 >> 4;
+          if (elect_one()) {
+            uint4 e = tap_tab[t0];
+            for (int tp = t0; tp < t1; ++tp) {
+              const uint4 nx = tap_tab[tp + 1 < t1 ? tp + 1 : tp];      // prefetch the next entry
+              const uint64_t da = sw128_hi | (uint64_t)(a0s + e.x);
+              const uint64_t db = sw128_hi | (uint64_t)(b0s + e.y);
+              const uint32_t dcol = tacc + e.z;
+              if (nch == 1) {
+                umma_bf16(dcol, da, db, idesc, !e.w);
+                umma_bf16(dcol, da + 2, db + 2, idesc, 1);
+                umma_bf16(dcol, da + 4, db + 4, idesc, 1);
+                umma_bf16(dcol, da + 6, db + 6, idesc, 1);
+              } else {
+                umma_bf16(dcol, da, db, idesc, !e.w);
+                umma_bf16(dcol + ch1, da + 2, db + 2, idesc, !e.w);
+                umma_bf16(dcol + ch2, da + 4, db + 4, idesc, !(e.w && nch > 2));
+                umma_bf16(dcol + ch3, da + 6, db + 6, idesc, !(e.w && nch > 2));
+              }
+              e = nx;
             }
           }
         } else if (d.pixel_pair_k) {
+          // One MMA per tap.  A serial per-tap chain (indexed constant loads -> descriptor -> uniform registers ->
+          // tcgen05.mma) cost ~370 cycles per MMA on this single warp (ncu: the issuer never waits on a barrier,
+          // the tensor pipe idles 65 %), so lane l holds the tile-invariant operands of tap l (built once per
+          // kernel, above) and the issue loop only broadcasts them with independent shuffles and adds the stage /
+          // TMEM-buffer bases.  One elected lane issues every MMA (a tcgen05.commit only tracks the MMAs of the
+          // thread that executes it).
+          const uint32_t a0s = a0 >> 4, b0s = b0 >> 4;
           for (int tp = t0; tp < t1; ++tp) {
-            const uint64_t da = make_noswz_desc(a0 + (uint32_t)d.tap_sx[tp], 16u);
-            const uint64_t db = sw128_hi | (uint64_t)((b0 + (uint32_t)d.tap_kstep[tp]) >> 4);
-            const int chain = nch > 1 ? (tp - t0) % nch : 0;   // 4 pair-taps per row -> up to 4 chains
-            if (elect_one())
-              umma_bf16(tacc + (uint32_t)d.tap_acc_col[tp] + (uint32_t)(chain * d.Ntot), da, db, idesc, !(kb == 0 && (tp - t0) < nch));
+            const uint32_t ta = __shfl_sync(0xffffffffu, pp_a, tp) + a0s;
+            const uint32_t tb = __shfl_sync(0xffffffffu, pp_b, tp) + b0s;
+            const uint32_t dc = __shfl_sync(0xffffffffu, pp_col, tp) + tacc;
+            const uint32_t ac = __shfl_sync(0xffffffffu, pp_acc, tp);
+            if (elect_one()) umma_bf16(dc, noswz_hi | ta, sw128_hi | tb, idesc, ac);
           }
         } else {
           for (int tp = t0; tp < t1; ++tp) {
@@ -291,6 +330,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         __syncwarp();
         if (elect_one()) umma_commit(empty_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
       __syncwarp();
       if (elect_one()) umma_commit(tfull_bar(buf));
@@ -484,6 +524,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   MSG_REQUIRE(d->n_kblocks >= 1 && d->n_kblocks <= MSG_SLAB_MAX_KBLOCKS && d->n_taps >= 1 && d->n_taps <= MSG_SLAB_MAX_TAPS &&
                   d->halo >= 0 && d->halo <= 16,
               MSG_ERR_SHAPE, "conv_slab: program too large");
+  MSG_REQUIRE(!d->pixel_pair_k || d->n_taps <= 32, MSG_ERR_SHAPE, "conv_slab: pixel-pair programs hold at most 32 taps");
   MSG_REQUIRE((((uintptr_t)x | (uintptr_t)w_slab) & 15) == 0, MSG_ERR_ALIGN, "conv_slab: operands must be 16-byte aligned");
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv_slab: stats buffer missing");
   EncodeTiledFn enc = get_encode();
@@ -530,7 +571,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 4 * 1056 * 4 + 1024 + 256 + 1024 + p.b_resident;
+  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 4 * 1056 * 4 + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_slab: stage of %d bytes does not fit twice in shared memory", stage_bytes);

@@ -82,6 +82,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -186,7 +198,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      bool wrapped = false;
       for (int t = t_begin; t < t_end; ++t) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int img = mt / (tile_rows * tiles_per_row);
@@ -197,37 +211,51 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         int kb = 0;
         for (int th = 0; th < d.KH; ++th)
           for (int tw = 0; tw < d.KW; ++tw)
-            for (int cb = 0; cb < p.cblocks; ++cb, ++kb, ++it) {
-              const int s = it % S;
-              if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
+            for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+              if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
               mbar_expect_tx(full_bar(s), A_BYTES + b_bytes);
               tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), cb * BK, w_base + tw * d.dil, h_base + th * d.dil, img);
               tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN);
+              if (++s == S) { s = 0; ph ^= 1u; wrapped = true; }   // no per-K-block div/mod by the runtime stage count
             }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // The issue loop is a single warp's serial instruction stream (~6 cycles per dependent instruction), and a K
+    // block of four N<=128 MMAs is only 128-256 tensor cycles: every instruction here is on the critical path.
+    // So: the whole warp runs the loop (warp-uniform values stay in uniform registers), stage / phase are counted
+    // incrementally (no div/mod by the runtime stage count), descriptors are one multiply-add from the stage
+    // index, and one elected lane issues the four MMAs and the commit of a K block.
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, lt = 0;
+      const uint64_t desc_hi = make_sw128_desc(0);
+      const uint32_t a_base = sA >> 4, b_base = sB >> 4;
+      const uint32_t a_step = A_BYTES >> 4, b_step = (uint32_t)b_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0, lt = 0;
       for (int t = t_begin; t < t_end; ++t, ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(full_bar(s), (it / S) & 1);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint64_t da = make_sw128_desc(sA + s * A_BYTES);
-          const uint64_t db = make_sw128_desc(sB + s * b_bytes);
-#pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4)
-            umma_bf16(tacc, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
-          umma_commit(empty_bar(s));
+          const uint64_t da = desc_hi | (uint64_t)(a_base + (uint32_t)s * a_step);
+          const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)s * b_step);
+          if (elect_one()) {
+            umma_bf16(tacc, da, db, idesc, kb != 0);
+            umma_bf16_acc(tacc, da + 2, db + 2, idesc);
+            umma_bf16_acc(tacc, da + 4, db + 4, idesc);
+            umma_bf16_acc(tacc, da + 6, db + 6, idesc);
+            umma_commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));
+        if (elect_one()) umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
     }
   } else {

@@ -11,6 +11,8 @@ Per stage (down1/down2/up1/up2, width C), kernels launched in the forward:
     4 branch convs writing channel slices of ONE [N,H,W,C] tensor (no cat) + shared IN statistics
     IN apply + ReLU -> fusion 1x1 conv (+ statistics) -> IN apply + ReLU + residual add
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -56,6 +58,7 @@ class GeneratorEngine:
         self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
         self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
         self._msb64_prog = slab.msb64_shift_program()
+        self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
 
     def _versions(self, params, names):
         return tuple((params[n].data_ptr(), params[n]._version) for n in names)
@@ -134,7 +137,8 @@ class GeneratorEngine:
             wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
             bn_ = [f"{s}.4.branch{i}.0.bias" for i in range(1, 5)]
             bsl = self._slab_cached(P, (s, "msb_b"), bn_, lambda: torch.cat([P[k].detach() for k in bn_]).contiguous())
-            if C == 64:     # taps-as-N: one MMA per (input row, K step), shifts applied in the epilogue (conv_shift.cu)
+            if C == 64 and self.msb64_taps_as_n:   # taps-as-N (conv_shift.cu): 1.09 ms vs 0.89 ms per 16 images at
+                # 512^2 for the per-tap slab kernel once its issue loop went lean, so off by default
                 wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb64_shift_weights([P[k].detach() for k in wn]))
                 slab.conv_shift(self._msb64_prog, a1, wsl, bsl, out=b, stats=stb)
             else:           # one MMA per tap on shifted views of the slab (conv_slab.cu)

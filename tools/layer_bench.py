@@ -71,7 +71,16 @@ def main():
             fl = 2.0 * N * Ho * Wo * Cout * Cin * k * k
         by = (x.numel() + out.numel()) * 2
         print(f"{name:32s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TF/s  {by / ms / 1e6:8.0f} GB/s")
-    if not a.only or "slab" in a.only:
+    if a.only == "slabin":
+        from multi_style_transfer_gan_b200 import slab
+        x8 = torch.randn(N, S, S, 8, device=dev).to(dt)
+        prog = slab.conv7_in_program(c)
+        wsl = slab.conv7_in_weight_slab(prog, torch.randn(c, 3, 7, 7, device=dev) * 0.1)
+        out = torch.empty(N, S, S, c, device=dev, dtype=dt)
+        st = ops.new_stats(N, c, dev)
+        ms = time_fn(lambda: slab.conv_slab(prog, x8, wsl, None, out=out, stats=st))
+        print(f"{'slab input 7x7 3(8)->64 @S':32s} {ms:8.3f} ms  {2.0 * N * S * S * c * 3 * 49 / ms / 1e9:8.1f} TF/s  {(x8.numel() + out.numel()) * 2 / ms / 1e6:8.0f} GB/s")
+    if not a.only or a.only == "slab":
         from multi_style_transfer_gan_b200 import slab
         for C, H in ((64, S), (128, S // 2), (256, S // 4)):
             x = torch.randn(N, H, H, C, device=dev).to(dt)
