@@ -266,7 +266,12 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                       # identical init on every rank
     c = args.channels
-    m = EnhancedCycleGAN(channels=c, num_transformer_blocks=3 if c == 64 else 1, precision=args.precision, device=dev)
+    style = None
+    if args.lambda_style > 0:                  # BASELINE config 4: + VGG-19 Gram style term (random-init trunk, seed 0)
+        from multi_style_transfer_gan_b200.style_loss import GramStyleLoss, VGG19Features
+        style = GramStyleLoss(VGG19Features(dev, seed=0), precision=args.precision)
+    m = EnhancedCycleGAN(channels=c, num_transformer_blocks=3 if c == 64 else 1, precision=args.precision, device=dev,
+                         style_loss=style, lambda_style=args.lambda_style)
     B, S = args.train_batch, args.train_size
     A = synth_images(B, S, S, seed=11 + rank).pin_memory()
     Bm = synth_images(B, S, S, seed=12 + rank).pin_memory()
@@ -295,8 +300,9 @@ def run_train(args):
         line = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": f"EnhancedCycleGAN.train_step (2 G + 2 D, LSGAN + cycle + identity + structure losses, "
-                                       f"fused Adam), c={c}, batch {B} per GPU at {S}x{S}", "global_batch": B * world,
+                "config": {"workload": f"EnhancedCycleGAN.train_step (2 G + 2 D, LSGAN + cycle + identity + structure losses"
+                                       + (f" + {args.lambda_style:g} x VGG-19 Gram style loss (random-init trunk)" if style else "")
+                                       + f", fused Adam), c={c}, batch {B} per GPU at {S}x{S}", "global_batch": B * world,
                            "parallelism": f"data-parallel x{world}, 2 flat NCCL all-reduces per step"},
                 "gpu_launches": _lib.launches - l0, "losses": losses,
                 "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": 2 * A.numel() * 4, "d2h_bytes_per_step": 20},
@@ -321,6 +327,8 @@ def main():
     ap.add_argument("--workload", default="stylise", choices=["stylise", "train"])
     ap.add_argument("--train-batch", type=int, default=8)
     ap.add_argument("--train-size", type=int, default=256)
+    ap.add_argument("--lambda-style", type=float, default=0.0,
+                    help="train workload: weight of the VGG-19 Gram style term (0 = the reference's train_step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

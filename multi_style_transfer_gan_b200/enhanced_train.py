@@ -11,6 +11,10 @@ Differences that are deliberate:
   * the reference leaks generator-phase gradients into D's .grad and discards them at the next
     zero_grad (:67); here they are simply not computed.
   * the data loop / dataset (enhanced_train.py:154-208) is out of scope: inputs are tensors.
+  * optional extension (north_star / BASELINE config 4, not in the reference): ``style_loss=GramStyleLoss(...)``
+    with ``lambda_style > 0`` adds lambda_style * (L_gram(fake_B | style real_B) + L_gram(fake_A | style real_A))
+    to the generator objective and a sixth key ``style_loss`` to the returned dict.  Default: off, so the
+    default step is the reference's.
 """
 from pathlib import Path
 
@@ -68,7 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
 
 class EnhancedCycleGAN:
     def __init__(self, pretrained_path=None, channels=16, num_transformer_blocks=1, precision="bf16",
-                 device=None):
+                 device=None, style_loss=None, lambda_style=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("EnhancedCycleGAN (msg_b200): a B200 GPU is required; there is no CPU path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -85,6 +89,9 @@ class EnhancedCycleGAN:
             self.G_BA.load_state_dict(ckpt["model_state_dict"], strict=False)
         self.set_precision(precision)
         self.lambda_cycle, self.lambda_identity, self.lambda_structure = 10.0, 2.0, 0.5   # :55-57
+        self.style_loss, self.lambda_style = style_loss, float(lambda_style)
+        if self.lambda_style > 0 and style_loss is None:
+            raise ValueError("lambda_style > 0 needs a style_loss (multi_style_transfer_gan_b200.style_loss.GramStyleLoss)")
         self._build_optimizers()
 
     def _build_optimizers(self):
@@ -153,6 +160,13 @@ class EnhancedCycleGAN:
         _, fake_B_struct = D_B(fake_B)
         structure_loss = (l1(real_A_struct, fake_A_struct) + l1(real_B_struct, fake_B_struct)) * self.lambda_structure
         total_g_loss = g_loss + cycle_loss + identity_loss + structure_loss
+        style_term = None
+        if self.lambda_style > 0:
+            # Gram style term on the translated images against the real images of the target domain (the targets
+            # are captured by the autograd node, so re-pointing the style between the two calls is safe)
+            sl = self.style_loss
+            style_term = (sl.set_style(real_B)(fake_B) + sl.set_style(real_A)(fake_A)) * self.lambda_style
+            total_g_loss = total_g_loss + style_term
         total_g_loss.backward()
         self.g_optimizer.step(grad_scale=self._sync_grads(self.g_optimizer))
         for m in (D_A, D_B):
@@ -160,9 +174,13 @@ class EnhancedCycleGAN:
         for m in (G_AB, G_BA):
             m.invalidate_packed_weights()
 
-        vals = torch.stack([d_loss.detach(), g_loss.detach(), cycle_loss.detach(), identity_loss.detach(),
-                            structure_loss.detach()]).tolist()          # one sync instead of five .item()
-        return dict(zip(("d_loss", "g_loss", "cycle_loss", "identity_loss", "structure_loss"), vals))
+        outs = [d_loss.detach(), g_loss.detach(), cycle_loss.detach(), identity_loss.detach(), structure_loss.detach()]
+        keys = ["d_loss", "g_loss", "cycle_loss", "identity_loss", "structure_loss"]
+        if style_term is not None:
+            outs.append(style_term.detach())
+            keys.append("style_loss")
+        vals = torch.stack(outs).tolist()          # one sync instead of five .item()
+        return dict(zip(keys, vals))
 
     def save_models(self, save_dir, epoch):
         """reference: enhanced_train.py:133-152 (same file names and dict keys)."""

@@ -5,6 +5,8 @@ All calls go model -> ctypes -> C-ABI -> sm_100a kernels.
 Tolerances (tests/util.py): forward outputs / losses <= 1e-4 (fp32 mode), image <= 2e-2 max-abs
 (bf16 mode) -- BASELINE.json.  Gradients: 1e-2, because the reference's own fp32 gradients are
 only reproducible to 1e-3..4e-3 against an fp64 evaluation of the same graph."""
+import math
+
 import pytest
 import torch
 
@@ -251,3 +253,63 @@ def test_save_models_layout(tmp_path):
     assert set(a) == {"epoch", "G_AB_state_dict"} and len(a["G_AB_state_dict"]) == 70
     d = torch.load(tmp_path / "discriminators_epoch_3.pth", weights_only=False)
     assert set(d) == {"epoch", "D_A_state_dict", "D_B_state_dict"} and len(d["D_A_state_dict"]) == 28
+
+
+def test_train_step_with_gram_style_term():
+    """north_star / BASELINE config 4 extension: lambda_style > 0 adds the VGG Gram term to the generator objective
+    (sixth dict key) and changes the generator update; the discriminator phase, which precedes it, is unaffected."""
+    from multi_style_transfer_gan_b200.enhanced_train import EnhancedCycleGAN
+    from multi_style_transfer_gan_b200.style_loss import GramStyleLoss, VGG19Features
+    torch.manual_seed(3)
+    A = torch.rand(2, 3, 64, 64) * 2 - 1
+    B = torch.rand(2, 3, 64, 64) * 2 - 1
+    outs, params = [], []
+    for lam in (0.0, 10.0):
+        torch.manual_seed(0)
+        style = GramStyleLoss(VGG19Features(DEV, seed=0), precision="fp32") if lam else None
+        m = EnhancedCycleGAN(channels=8, precision="fp32", device=DEV, style_loss=style, lambda_style=lam)
+        outs.append(m.train_step(A, B))
+        params.append(m.g_optimizer.flat.clone())
+    assert set(outs[0]) == {"d_loss", "g_loss", "cycle_loss", "identity_loss", "structure_loss"}
+    assert set(outs[1]) == set(outs[0]) | {"style_loss"}
+    assert outs[1]["style_loss"] > 0 and math.isfinite(outs[1]["style_loss"])
+    for k in outs[0]:
+        assert abs(outs[0][k] - outs[1][k]) <= 1e-5 * max(1.0, abs(outs[0][k])), k
+    assert float((params[0] - params[1]).abs().max()) > 0
+    with pytest.raises(ValueError):
+        EnhancedCycleGAN(channels=8, device=DEV, lambda_style=1.0)
+
+
+def test_config5_highres_four_style_blend_properties():
+    """BASELINE config 5 (1024x1024, 4 blended styles, bf16) at B=2 through size-independent properties: the
+    stylizer's output is the linear blend of the four single-style outputs, it does not depend on how the batch is
+    cut into micro-batches or on the other images in the batch, host-in/uint8-out equals device-in + manual
+    conversion, and the peak activation footprint stays far below one GPU's HBM."""
+    from multi_style_transfer_gan_b200 import ops
+    from multi_style_transfer_gan_b200.enhanced_generator import EnhancedGenerator
+    from multi_style_transfer_gan_b200.stylize import MultiStyleStylizer
+    from oracle import restate as R
+    gens = []
+    for s in range(4):
+        torch.manual_seed(s)
+        gens.append(EnhancedGenerator(channels=16, num_transformer_blocks=1).to(DEV))
+    w = [0.4, 0.3, 0.2, 0.1]
+    torch.manual_seed(1234)
+    x = (torch.rand(2, 3, 1024, 1024) * 2 - 1).to(DEV)
+    torch.cuda.reset_peak_memory_stats()
+    st = MultiStyleStylizer(gens, precision="bf16", micro_batch=2)
+    y = st(x, w)
+    peak = torch.cuda.max_memory_allocated()
+    assert y.shape == x.shape and torch.isfinite(y).all() and float(y.abs().max()) <= 1.0 + 1e-6
+    assert peak < 40 * 2 ** 30, peak
+    singles = [st.generators[s](x) for s in range(4)]
+    ref = R.blend_outputs([t.float().cpu() for t in singles], w)
+    assert_parity(y, ref, 1e-6, "blend of singles")
+    y1 = MultiStyleStylizer(gens, precision="bf16", micro_batch=1)(x, w)
+    assert torch.equal(y1, y), "micro-batching changed the result"
+    y0 = MultiStyleStylizer(gens, precision="bf16", micro_batch=2)(x[:1].contiguous(), w)
+    assert torch.equal(y0, y[:1]), "an image's result depends on its batch neighbours"
+    u8 = torch.empty(2, 3, 1024, 1024, dtype=torch.uint8).pin_memory()
+    st(x.cpu().pin_memory(), w, out_uint8=True, out=u8)
+    torch.cuda.synchronize()
+    assert (u8.int() - R.to_uint8_image(y.cpu()).int()).abs().max() <= 1
