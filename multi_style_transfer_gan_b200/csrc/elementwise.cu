@@ -1,6 +1,10 @@
 // Bandwidth-bound helpers around the conv path: layout conversion at the module boundary,
 // the multi-style output blend, losses, fused Adam, spectral-norm power iteration, pooling.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace msg {
 namespace {
@@ -128,8 +132,14 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 // ---- spectral norm --------------------------------------------------------------------------
-// single CTA (matrices are at most 512 x 4608): v = normalize(W^T u); u = normalize(W v);
-// sigma = u^T W v.  1024 threads; dynamic smem holds a rows-sized scratch.
+// One power iteration (old-style torch.nn.utils.spectral_norm, enhanced_generator.py:269-271):
+//   v = normalize(W^T u); u = normalize(W v); sigma = u^T W v.
+// The two passes over W (up to 512 x 4608 fp32 = 9 MB) used to run on ONE CTA (160 us per call, 9.6 ms per
+// train step).  Now one thread-block CLUSTER of 8 CTAs shares the work: columns (pass 1) and rows (pass 2) are
+// split over the 8192 threads, the three norms are reduced through distributed shared memory, and the two
+// cluster barriers order the global v / u hand-over between the CTAs.
+constexpr int SN_CLUSTER = 8;
+constexpr int SN_TPB = 1024;
 __device__ float block_sum_1024(float v, float* red) {
   v = warp_sum(v);
   __syncthreads();
@@ -139,47 +149,73 @@ __device__ float block_sum_1024(float v, float* red) {
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
   return t;
 }
-__global__ void __launch_bounds__(1024)
+__device__ __forceinline__ float cluster_total(cg::cluster_group& cl, float* slot, float mine) {
+  // every CTA publishes its partial in its own smem slot, then sums the 8 slots over DSMEM
+  if (threadIdx.x == 0) *slot = mine;
+  cl.sync();
+  float t = 0.f;
+  for (int r = 0; r < SN_CLUSTER; ++r) t += *cl.map_shared_rank(slot, r);
+  return t;
+}
+__global__ void __cluster_dims__(SN_CLUSTER, 1, 1) __launch_bounds__(SN_TPB)
 spectral_norm_kernel(const float* __restrict__ w, int rows, int cols, float* __restrict__ u,
                      float* __restrict__ v, int do_iter, float eps, float* __restrict__ sigma) {
   __shared__ float red[32];
-  extern __shared__ float wv[];  // [rows]
-  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ float part[3];
+  cg::cluster_group cl = cg::this_cluster();
+  const int tid = threadIdx.x, cta = (int)cl.block_rank();
+  const int gtid = cta * SN_TPB + tid, gthreads = SN_CLUSTER * SN_TPB;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gwarp = cta * (SN_TPB / 32) + warp, gwarps = SN_CLUSTER * (SN_TPB / 32);
+  float vscale = 1.f;                     // v is kept un-normalised in global memory until the end
   if (do_iter) {
-    // v = W^T u (column j: sum_r w[r][j] u[r]) -- coalesced over j
+    // pass 1: v_raw = W^T u (column j: sum_r w[r][j] u[r]) -- coalesced over j
     float ss = 0.f;
-    for (int j = tid; j < cols; j += nt) {
-      float a = 0.f;
-      for (int r = 0; r < rows; ++r) a = fmaf(w[(size_t)r * cols + j], u[r], a);
+    for (int j = gtid; j < cols; j += gthreads) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;           // 8 loads in flight per thread (latency-bound otherwise)
+      int r = 0;
+      for (; r + 8 <= rows; r += 8) {
+        const float* wp = w + (size_t)r * cols + j;
+        const float w0 = wp[0], w1 = wp[cols], w2 = wp[2 * (size_t)cols], w3 = wp[3 * (size_t)cols];
+        const float w4 = wp[4 * (size_t)cols], w5 = wp[5 * (size_t)cols], w6 = wp[6 * (size_t)cols], w7 = wp[7 * (size_t)cols];
+        a0 = fmaf(w0, u[r], a0); a1 = fmaf(w1, u[r + 1], a1); a2 = fmaf(w2, u[r + 2], a2); a3 = fmaf(w3, u[r + 3], a3);
+        a0 = fmaf(w4, u[r + 4], a0); a1 = fmaf(w5, u[r + 5], a1); a2 = fmaf(w6, u[r + 6], a2); a3 = fmaf(w7, u[r + 7], a3);
+      }
+      for (; r < rows; ++r) a0 = fmaf(w[(size_t)r * cols + j], u[r], a0);
+      const float a = (a0 + a1) + (a2 + a3);
       v[j] = a;
       ss = fmaf(a, a, ss);
     }
     ss = block_sum_1024(ss, red);
-    float inv = 1.f / fmaxf(sqrtf(ss), eps);
-    for (int j = tid; j < cols; j += nt) v[j] *= inv;
-    __syncthreads();
+    ss = cluster_total(cl, &part[0], ss);                     // barrier: every v_raw[j] and u read is done
+    vscale = 1.f / fmaxf(sqrtf(ss), eps);
   }
-  // wv = W v : one warp per row
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  for (int r = warp; r < rows; r += nw) {
+  // pass 2: wv = W v : one warp per row; raw W v_raw goes to a register, scaled by 1/|v_raw|
+  float ss2 = 0.f, dot = 0.f;
+  for (int r = gwarp; r < rows; r += gwarps) {
     float a = 0.f;
     for (int j = lane; j < cols; j += 32) a = fmaf(w[(size_t)r * cols + j], v[j], a);
-    a = warp_sum(a);
-    if (lane == 0) wv[r] = a;
+    a = warp_sum(a) * vscale;
+    if (do_iter) {
+      if (lane == 0) { u[r] = a; ss2 = fmaf(a, a, ss2); }     // u_raw = W v; the old u is no longer needed
+    } else if (lane == 0) {
+      dot = fmaf(u[r], a, dot);
+    }
   }
-  __syncthreads();
   if (do_iter) {
-    float ss = 0.f;
-    for (int r = tid; r < rows; r += nt) ss = fmaf(wv[r], wv[r], ss);
-    ss = block_sum_1024(ss, red);
-    float inv = 1.f / fmaxf(sqrtf(ss), eps);
-    for (int r = tid; r < rows; r += nt) u[r] = wv[r] * inv;
-    __syncthreads();
+    ss2 = block_sum_1024(ss2, red);
+    ss2 = cluster_total(cl, &part[1], ss2);                   // barrier: all of v_raw has been consumed
+    const float inv = 1.f / fmaxf(sqrtf(ss2), eps);
+    for (int r = gwarp; r < rows; r += gwarps)                // each warp rescales the rows it produced
+      if (lane == 0) u[r] *= inv;
+    for (int j = gtid; j < cols; j += gthreads) v[j] *= vscale;   // each thread rescales the columns it produced
+    if (gtid == 0) *sigma = ss2 * inv;                        // u^T (W v) = |W v|^2 / |W v|
+  } else {
+    dot = block_sum_1024(dot, red);
+    dot = cluster_total(cl, &part[2], dot);
+    if (gtid == 0) *sigma = dot;
   }
-  float d = 0.f;
-  for (int r = tid; r < rows; r += nt) d = fmaf(u[r], wv[r], d);
-  d = block_sum_1024(d, red);
-  if (tid == 0) *sigma = d;
+  cl.sync();                                                  // no CTA may exit while its smem slot can still be read
 }
 // scratch[0] = <dw, w_orig>
 __global__ void __launch_bounds__(EW_TPB)
@@ -364,8 +400,8 @@ extern "C" int msg_adam_step(float* p, const float* g, float* m, float* v, long 
 
 extern "C" int msg_spectral_norm(const float* w, int rows, int cols, float* u, float* v,
                                  int do_power_iter, float eps, float* sigma, void* stream) {
-  MSG_REQUIRE(rows > 0 && cols > 0 && rows <= 8192, MSG_ERR_SHAPE, "spectral_norm: bad shape");
-  spectral_norm_kernel<<<1, 1024, rows * sizeof(float), as_stream(stream)>>>(w, rows, cols, u, v, do_power_iter, eps, sigma);
+  MSG_REQUIRE(rows > 0 && cols > 0, MSG_ERR_SHAPE, "spectral_norm: bad shape");
+  spectral_norm_kernel<<<SN_CLUSTER, SN_TPB, 0, as_stream(stream)>>>(w, rows, cols, u, v, do_power_iter, eps, sigma);
   return check_launch("spectral_norm_kernel");
 }
 extern "C" int msg_spectral_norm_bwd(const float* dw, const float* w_orig, const float* u,

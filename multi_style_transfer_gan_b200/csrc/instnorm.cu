@@ -3,6 +3,8 @@
 // Bandwidth-bound: 16-byte vector accesses, per-thread channel groups fixed across the pixel loop
 // (so scale/shift live in registers), block reduction in shared memory, one atomic per
 // (block, channel).   Reference: nn.InstanceNorm2d at enhanced_generator.py:54..129, 242..263.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace msg {
@@ -353,7 +355,8 @@ int apply_impl(const T* x, const double* stats, int N, long long HW, int C, int 
                int S, const float* gammas, const float* betas, const float* w, T* y, cudaStream_t st) {
   if (fast_ok<T>(C, HW)) {
     const long long nvec = HW * C / Vec<T>::W;
-    long long want = (4LL * sm_count() + N - 1) / N;           // ~4 CTAs per SM over the whole launch
+    static const int ctas_per_sm = [] { const char* e = getenv("MSG_IN_CTAS"); return e ? atoi(e) : 4; }();
+    long long want = ((long long)ctas_per_sm * sm_count() + N - 1) / N;   // ~4 CTAs per SM over the whole launch
     long long maxb = (nvec + TPB * 4 - 1) / (TPB * 4);         // >= 4 vectors per thread
     if (want > maxb) want = maxb;
     if (want < 1) want = 1;
