@@ -133,6 +133,8 @@ struct SlabParams {
   int b_box_taps;     // streaming mode: weight tiles fetched per TMA box
   int chunks;         // K chunks per slab (8, or 1 in pixel-pair mode)
   int segs;           // 128-pixel segments per image row
+  int a_rows;         // pixel-pair mode: input rows per slab (consecutive filter rows fused into ONE K block)
+  int b_tiles;        // weight tiles in w_slab (= taps, or filter rows in pixel-pair mode)
   int a_mode;         // 0: chunk planes [chunk][pixel][16 B], no swizzle (8 TMA boxes per slab)
                       // 1: pixel rows [pixel][128 B], 128B swizzle, ONE TMA box; tap shift = +128 B/pixel on the
                       //    descriptor start, swizzle phase carried by the descriptor's base_offset field
@@ -194,7 +196,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       if (p.b_resident) {       // all weight tiles, once: they stay in smem for every tile of this CTA
-        const int tiles_total = d.pixel_pair_k ? d.n_kblocks : d.n_taps;
+        const int tiles_total = p.b_tiles;
         mbar_expect_tx(wres_bar, (uint32_t)(((tiles_total + p.b_box_taps - 1) / p.b_box_taps) * p.b_box_taps * tap_bytes));
         for (int bx = 0; bx * p.b_box_taps < tiles_total; ++bx)
           tma_load_2d(sB + bx * p.b_box_taps * tap_bytes, &mapB, wres_bar, 0, bx * p.b_box_taps * d.ncols);
@@ -568,6 +570,24 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
       if (d->pixel_pair_k) p.d.tap_kstep[tp] = d->tap_kstep[tp] * 32 + (p.b_resident ? kb * tap_bytes : 0);
       else p.d.tap_kstep[tp] = (p.b_resident ? tp : tp - d->kb_tap_begin[kb]) * tap_bytes;
     }
+  p.a_rows = 1;
+  p.b_tiles = n_tiles_total;
+  if (d->pixel_pair_k && p.b_resident && d->n_kblocks > 1) {
+    // Consecutive filter rows -> ONE K block: a single TMA box {8 ch, Ws, rows} brings every input row of the tile
+    // (out-of-image rows zero-filled), the issuer runs all taps back to back and commits once, instead of one
+    // barrier round trip per filter row (the issuing warp's serial instruction stream is the bottleneck here).
+    bool consecutive = true;
+    for (int kb = 1; kb < d->n_kblocks; ++kb)
+      consecutive = consecutive && d->kb_dy[kb] == d->kb_dy[0] + kb && d->kb_cb[kb] == d->kb_cb[0];
+    if (consecutive && d->n_kblocks * p.a_bytes <= 32 * 1024) {
+      for (int kb = 0; kb < d->n_kblocks; ++kb)
+        for (int tp = d->kb_tap_begin[kb]; tp < d->kb_tap_begin[kb + 1]; ++tp) p.d.tap_sx[tp] += kb * p.a_bytes;
+      p.a_rows = d->n_kblocks;
+      p.a_bytes *= d->n_kblocks;
+      p.d.n_kblocks = 1;
+      p.d.kb_tap_begin[1] = d->n_taps;
+    }
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
@@ -583,7 +603,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->W * d->Ci_total * 2,
                              (cuuint64_t)d->H * d->W * d->Ci_total * 2};
-    cuuint32_t box[4] = {(cuuint32_t)(p.a_mode != 0 ? 64 : 8), (cuuint32_t)p.Ws, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(p.a_mode != 0 ? 64 : 8), (cuuint32_t)p.Ws, (cuuint32_t)p.a_rows, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = (void*)((const __nv_bfloat16*)x + d->ci_off);
     CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
