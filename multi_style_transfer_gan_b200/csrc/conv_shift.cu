@@ -113,8 +113,8 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const uint32_t sB = base;                                   // resident weights [b_rows][128 B], SW128
   const uint32_t sA = sB + p.b_bytes;                         // slab ring
   const uint32_t sEx = sA + S * A_BYTES;                      // exchange tile [128][Ntot + 4] floats
-  const uint32_t sSum = sEx + BM * p.ex_pitch * 4;              // per-warp column sums [4][2][64] floats
-  const uint32_t sTr = sSum + 4 * 128 * 4;                    // per-warp transpose scratch [4][32][33]
+  const uint32_t sSum = (sEx + BM * p.ex_pitch * 4 + 7u) & ~7u;  // per-warp column sums [4][2][64] doubles
+  const uint32_t sTr = sSum + 4 * 128 * 8;                    // per-warp transpose scratch [4][32][33]
   const uint32_t sBias = sTr + 4 * 1056 * 4;                  // bias [<= 256]
   const uint32_t sBar = (sBias + 1024 + 7u) & ~7u;
   float* ex = reinterpret_cast<float*>(gen + (sEx - base));
@@ -220,18 +220,18 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int row = q * 32 + lane;                // slab pixel held by this thread (TMEM lane)
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
-    float* wsum = reinterpret_cast<float*>(gen + (sSum - base)) + q * 128;    // [2][64]
+    double* wsum = reinterpret_cast<double*>(gen + (sSum - base)) + q * 128;  // [2][64], fp64 above the 32-row partials
     float* tr = reinterpret_cast<float*>(gen + (sTr - base)) + q * 1056;      // [32][33]
-    for (int i = lane; i < 128; i += 32) wsum[i] = 0.f;
+    for (int i = lane; i < 128; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < d.n_out; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
-          atomicAdd(st, (double)wsum[c]);
-          atomicAdd(st + 1, (double)wsum[64 + c]);
-          wsum[c] = 0.f; wsum[64 + c] = 0.f;
+          atomicAdd(st, wsum[c]);
+          atomicAdd(st + 1, wsum[64 + c]);
+          wsum[c] = 0.0; wsum[64 + c] = 0.0;
         }
       }
       __syncwarp();
@@ -299,7 +299,7 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             float cs = 0.f, css = 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
-            if (lane < oc) { wsum[oc0 + lane] += cs; wsum[64 + oc0 + lane] += css; }
+            if (lane < oc) { wsum[oc0 + lane] += (double)cs; wsum[64 + oc0 + lane] += (double)css; }
           }
           __syncwarp();
         }
@@ -411,7 +411,7 @@ extern "C" int msg_conv_shift(const msg_shift_desc* d, const void* x, const void
                 "conv_shift: group %d reads past the TMEM allocation", g);
   p.ex_pitch = ((d->Ntot + 3) / 4) * 4 + 4;      // 16-byte aligned rows, pitch % 32 floats == 4: conflict-free float4 access
   if (p.ex_pitch % 32 != 4) p.ex_pitch += (4 - p.ex_pitch % 32 + 32) % 32;
-  const int fixed = p.b_bytes + BM * p.ex_pitch * 4 + 4 * 128 * 4 + 4 * 1056 * 4 + 1024 + 256 + 1024;
+  const int fixed = p.b_bytes + BM * p.ex_pitch * 4 + 8 + 4 * 128 * 8 + 4 * 1056 * 4 + 1024 + 256 + 1024;
   int stages = (220 * 1024 - fixed) / A_BYTES;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_shift: not enough shared memory for the slab ring");

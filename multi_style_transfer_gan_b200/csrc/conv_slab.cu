@@ -154,7 +154,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t sA = sB + (p.b_resident ? p.b_resident : S * p.b_bytes);
   const uint32_t sStage = (sA + S * p.a_bytes + 127u) & ~127u;
   const uint32_t sRed = sStage + 4 * 32 * STAGE_PITCH;        // per-warp column sums [4][2][256] floats
-  const uint32_t sBias = sRed + 8192 + 4 * 1056 * 4;                         // bias staged once per CTA (Ntot <= 256 floats)
+  const uint32_t sBias = sRed + 16384 + 4 * 1056 * 4;                        // bias staged once per CTA (Ntot <= 256 floats)
   const uint32_t sBar = sBias + 1024;
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
@@ -345,18 +345,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
     uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
-    float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
-    float* tr = red + 2048 + q * 1056;            // [32][33] transpose scratch of this warp
-    for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
+    double* wsum = reinterpret_cast<double*>(red) + q * 512;   // [2][256] running column sums of this warp (fp64 above the
+                                                               // fixed-order 32-row fp32 partials: grouping-independent)
+    float* tr = red + 4096 + q * 1056;            // [32][33] transpose scratch of this warp
+    for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < cmax; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
-          atomicAdd(st, (double)wsum[c]);
-          atomicAdd(st + 1, (double)wsum[256 + c]);
-          wsum[c] = 0.f; wsum[256 + c] = 0.f;
+          atomicAdd(st, wsum[c]);
+          atomicAdd(st + 1, wsum[256 + c]);
+          wsum[c] = 0.0; wsum[256 + c] = 0.0;
         }
       }
       __syncwarp();
@@ -419,8 +420,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
               for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
               __syncwarp();
-              wsum[cg + h * 32 + lane] += cs;
-              wsum[256 + cg + h * 32 + lane] += css;
+              wsum[cg + h * 32 + lane] += (double)cs;
+              wsum[256 + cg + h * 32 + lane] += (double)css;
             }
           }
         }
@@ -591,7 +592,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 8192 + 4 * 1056 * 4 + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
+  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 16384 + 4 * 1056 * 4 + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_slab: stage of %d bytes does not fit twice in shared memory", stage_bytes);

@@ -32,7 +32,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;          // producer + MMA warp + up to two epilogue groups of four warps
+constexpr int EPI_FIXED = 16384 + 4 * 1056 * 4;  // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][33]
 constexpr int STAGE_PITCH = 128 + 16;   // manual flush: 64 bf16 columns per row + 16 B skew
 constexpr int STAGE_BYTES = 2 * BM * 128;   // two [128 rows x 64 cols] bf16 TMA-store buffers (SW128)
 
@@ -136,6 +137,7 @@ struct TmaParams {
   void* y;
   double* stats;
   int BN, n_tiles, m_tiles, stages, tmem_cols;
+  int epi_groups;     // 1: warps 2-5 drain both accumulator buffers; 2: warps 2-5 own buffer 0, warps 6-9 buffer 1
   int Wt, R;            // M tile = R rows x Wt pixels
   int cblocks;          // Cin / 64
   int nkb;              // KH*KW*cblocks
@@ -155,15 +157,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t sA = base;
   const uint32_t sB = sA + S * A_BYTES;
   const uint32_t sStage = sB + S * b_bytes;                 // epilogue staging, 1024-byte aligned
-  const uint32_t sRed = sStage + STAGE_BYTES;               // per-warp column sums [4][2][256] floats
-  const uint32_t sBias = sRed + 8192 + 4 * 1056 * 4;                       // bias staged once per CTA (<= 1024 floats)
+  const uint32_t sRed = sStage + p.epi_groups * STAGE_BYTES;              // per-warp column sums / transpose scratch
+  const uint32_t sBias = sRed + p.epi_groups * EPI_FIXED;                 // bias staged once per CTA (<= 1024 floats)
   const uint32_t sBar = sBias + 4096;                       // full[S], empty[S], tfull[2], tempty[2]
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
   float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
   const bool bias_in_smem = p.bias != nullptr && d.Cout <= 1024;
   if (bias_in_smem)
-    for (int i = tid; i < d.Cout; i += NTHREADS) sbias[i] = p.bias[i];
+    for (int i = tid; i < d.Cout; i += (int)blockDim.x) sbias[i] = p.bias[i];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
@@ -258,9 +260,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else {
-    // ===================================== epilogue (warps 2-5) =====================================
+  } else if (((warp - 2) >> 2) < p.epi_groups) {
+    // ===================================== epilogue (warps 2-5, and 6-9 with two groups) ===========
+    // The epilogue of a 128 x BN tile is a single warp's instruction stream per 32 rows (~550 instructions per 64
+    // columns with bias + statistics): with one warp per scheduler it is latency-bound and, for the 1x1 convs
+    // (one K block per tile), the whole kernel's bottleneck.  With two groups, group g drains accumulator buffer g,
+    // i.e. every other tile, so two epilogues are in flight per scheduler.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;              // epilogue group
+    const int G = p.epi_groups;
     const int row = q * 32 + lane;                // row of the M tile
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
@@ -268,29 +276,33 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int hw = d.Hg * d.Wg;
     // this warp's staging slice: 8 KB = two [32 rows x 128 B] TMA-store buffers (1024-byte aligned), also
     // used as the skewed [32 x 144 B] tile of the manual flush
-    uint8_t* stage_w = stage_gen + q * 8192;
-    const uint32_t stage_w_s = sStage + q * 8192;
-    float* wsum = red + q * 512;                  // [2][256] running column sums of this warp
-    float* tr = red + 2048 + q * 1056;            // [32][33] transpose scratch of this warp
-    for (int i = lane; i < 512; i += 32) wsum[i] = 0.f;
+    uint8_t* stage_w = stage_gen + (grp * 4 + q) * 8192;
+    const uint32_t stage_w_s = sStage + (grp * 4 + q) * 8192;
+    // running column sums of this warp, [2][256], in fp64: the 32-row partial sums are formed in fp32 in a fixed
+    // order, everything above that is fp64, so an image's statistics do not depend on how tiles were grouped per CTA
+    // (batch size, epilogue groups) beyond fp64 rounding
+    double* wsum = reinterpret_cast<double*>(red + grp * (EPI_FIXED / 4)) + q * 512;
+    float* tr = red + grp * (EPI_FIXED / 4) + 4096 + q * 1056;            // [32][33] transpose scratch of this warp
+    for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1, stat_nt = -1, stat_cmax = 0;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < stat_cmax; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + stat_nt * BN + c) * 2;
-          atomicAdd(st, (double)wsum[c]);
-          atomicAdd(st + 1, (double)wsum[256 + c]);
-          wsum[c] = 0.f; wsum[256 + c] = 0.f;
+          atomicAdd(st, wsum[c]);
+          atomicAdd(st + 1, wsum[256 + c]);
+          wsum[c] = 0.0; wsum[256 + c] = 0.0;
         }
       }
       __syncwarp();
     };
     uint32_t lt = 0, sgrp = 0;                    // tiles done, TMA-store groups issued by this warp
     bool tma_pending = false;                     // (lane 0) bulk groups possibly still reading smem
-    for (int t = t_begin; t < t_end; ++t, ++lt) {
+    for (int t = t_begin + (G == 2 ? grp : 0); t < t_end; t += G, ++lt) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-      const int buf = lt & 1;
+      const int buf = G == 2 ? grp : (int)(lt & 1);                      // accumulator buffer of this tile
+      const uint32_t tf_parity = G == 2 ? (lt & 1) : ((lt >> 1) & 1);    // its (lt or lt/2)-th use
       const long long m0 = (long long)mt * BM;
       const int co0 = nt * BN;
       const int cmax = (d.Cout - co0) < BN ? (d.Cout - co0) : BN;
@@ -309,7 +321,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         flush_stats();
         stat_img = n_img; stat_nt = nt; stat_cmax = cmax;
       }
-      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      mbar_wait(tfull_bar(buf), tf_parity);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
       for (int cg = 0; cg < cmax; cg += 64) {
@@ -350,8 +362,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
               for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
               __syncwarp();
-              wsum[cg + h * 32 + lane] += cs;
-              wsum[256 + cg + h * 32 + lane] += css;
+              wsum[cg + h * 32 + lane] += (double)cs;
+              wsum[256 + cg + h * 32 + lane] += (double)css;
             }
           }
         }
@@ -527,7 +539,16 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int K = d->KH * d->KW * d->Cin;
   const int stage_bytes = A_BYTES + p.BN * BK * 2;
-  const int fixed = STAGE_BYTES + 8192 + 4 * 1056 * 4 + 4096 + 8 * 16 + 64 + 1024;
+  // two epilogue groups when the extra staging / scratch (57 KB) still leaves >= 3 pipeline stages
+  static const int env_groups = [] { const char* e = getenv("MSG_TMA_EPI_GROUPS"); return e ? atoi(e) : 0; }();
+  {
+    const int st2 = (220 * 1024 - (2 * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024)) / stage_bytes;
+    // K-heavy tiles (many K blocks per tile) are L2->SM-bound and want the deep ring; the 1x1 convs (<= 4 K blocks
+    // per tile) are epilogue-bound and fine with 2 stages
+    p.epi_groups = (st2 >= 5 || (st2 >= 2 && p.nkb <= 4)) ? 2 : 1;
+  }
+  if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
+  const int fixed = p.epi_groups * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024;
   static const bool env_tstore = [] { const char* e = getenv("MSG_TMA_STORE"); return !(e && e[0] == '0'); }();
   p.tstore = (env_tstore && !(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
               d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&
@@ -581,7 +602,7 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   int grid = sm_count();
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
-  conv_tma_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p);
+  conv_tma_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(mapA, mapB, mapC, p);
   return check_launch("conv_tma_kernel");
 }
 
