@@ -137,6 +137,7 @@ struct TmaParams {
   void* y;
   double* stats;
   int BN, n_tiles, m_tiles, stages, tmem_cols;
+  int b_resident;     // 1: all nkb weight tiles of the (single) N tile stay in smem for the whole kernel
   int epi_groups;     // 1: warps 2-5 drain both accumulator buffers; 2: warps 2-5 own buffer 0, warps 6-9 buffer 1
   int Wt, R;            // M tile = R rows x Wt pixels
   int cblocks;          // Cin / 64
@@ -156,7 +157,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sA = base;
   const uint32_t sB = sA + S * A_BYTES;
-  const uint32_t sStage = sB + S * b_bytes;                 // epilogue staging, 1024-byte aligned
+  const uint32_t sStage = sB + (p.b_resident ? p.nkb : S) * b_bytes;   // epilogue staging, 1024-byte aligned
   const uint32_t sRed = sStage + p.epi_groups * STAGE_BYTES;              // per-warp column sums / transpose scratch
   const uint32_t sBias = sRed + p.epi_groups * EPI_FIXED;                 // bias staged once per CTA (<= 1024 floats)
   const uint32_t sBar = sBias + 4096;                       // full[S], empty[S], tfull[2], tempty[2]
@@ -166,7 +167,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const bool bias_in_smem = p.bias != nullptr && d.Cout <= 1024;
   if (bias_in_smem)
     for (int i = tid; i < d.Cout; i += (int)blockDim.x) sbias[i] = p.bias[i];
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 4));
+  const uint32_t wres_bar = sBar + 8u * (2 * S + 4);        // "resident weights have landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
   auto tfull_bar = [&](int b) { return sBar + 8u * (2 * S + b); };
@@ -176,6 +178,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+      mbar_init(wres_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -200,6 +203,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      if (p.b_resident) {      // one N tile and few K blocks: the weights are loaded once and never re-streamed
+        mbar_expect_tx(wres_bar, (uint32_t)(p.nkb * b_bytes));
+        for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + kb * b_bytes, &mapB, wres_bar, kb * BK, 0);
+      }
       int s = 0;
       uint32_t ph = 0;
       bool wrapped = false;
@@ -215,9 +222,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           for (int tw = 0; tw < d.KW; ++tw)
             for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
               if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
-              mbar_expect_tx(full_bar(s), A_BYTES + b_bytes);
+              mbar_expect_tx(full_bar(s), A_BYTES + (p.b_resident ? 0 : b_bytes));
               tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), cb * BK, w_base + tw * d.dil, h_base + th * d.dil, img);
-              tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN);
+              if (!p.b_resident) tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN);
               if (++s == S) { s = 0; ph ^= 1u; wrapped = true; }   // no per-K-block div/mod by the runtime stage count
             }
       }
@@ -236,6 +243,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t a_step = A_BYTES >> 4, b_step = (uint32_t)b_bytes >> 4;
       int s = 0;
       uint32_t ph = 0, lt = 0;
+      if (p.b_resident) mbar_wait(wres_bar, 0);
       for (int t = t_begin; t < t_end; ++t, ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
@@ -245,7 +253,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint64_t da = desc_hi | (uint64_t)(a_base + (uint32_t)s * a_step);
-          const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)s * b_step);
+          const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)(p.b_resident ? kb : s) * b_step);
           if (elect_one()) {
             umma_bf16(tacc, da, db, idesc, kb != 0);
             umma_bf16_acc(tacc, da + 2, db + 2, idesc);
@@ -538,23 +546,26 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int K = d->KH * d->KW * d->Cin;
-  const int stage_bytes = A_BYTES + p.BN * BK * 2;
+  static const bool env_bres = [] { const char* e = getenv("MSG_TMA_BRESIDENT"); return !(e && e[0] == '0'); }();
+  p.b_resident = (env_bres && p.n_tiles == 1 && p.nkb * p.BN * BK * 2 <= 64 * 1024) ? 1 : 0;
+  const int bres_bytes = p.b_resident ? p.nkb * p.BN * BK * 2 : 0;
+  const int stage_bytes = A_BYTES + (p.b_resident ? 0 : p.BN * BK * 2);
   // two epilogue groups when the extra staging / scratch (57 KB) still leaves >= 3 pipeline stages
   static const int env_groups = [] { const char* e = getenv("MSG_TMA_EPI_GROUPS"); return e ? atoi(e) : 0; }();
   {
-    const int st2 = (220 * 1024 - (2 * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024)) / stage_bytes;
+    const int st2 = (220 * 1024 - bres_bytes - (2 * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024)) / stage_bytes;
     // K-heavy tiles (many K blocks per tile) are L2->SM-bound and want the deep ring; the 1x1 convs (<= 4 K blocks
     // per tile) are epilogue-bound and fine with 2 stages
     p.epi_groups = (st2 >= 5 || (st2 >= 2 && p.nkb <= 4)) ? 2 : 1;
   }
   if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
-  const int fixed = p.epi_groups * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024;
+  const int fixed = p.epi_groups * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024 + bres_bytes;
   static const bool env_tstore = [] { const char* e = getenv("MSG_TMA_STORE"); return !(e && e[0] == '0'); }();
   p.tstore = (env_tstore && !(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
               d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&
               (((uintptr_t)y) & 15) == 0) ? 1 : 0;
   int stages = (220 * 1024 - fixed) / stage_bytes;
-  if (stages > 6) stages = 6;
+  if (stages > (p.b_resident ? 8 : 6)) stages = p.b_resident ? 8 : 6;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
