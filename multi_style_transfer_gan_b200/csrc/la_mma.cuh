@@ -1,6 +1,7 @@
 // Warp-level mma.sync / ldmatrix / cp.async helpers shared by the LocalAttention tensor-core kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace msg {
@@ -33,6 +34,34 @@ __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
   uint32_t y;
   asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {     // MUFU path
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+// 2^x for |x| <= 1.46 (cosine logits times log2 e) on the FMA pipe: degree-4 relative-minimax polynomial, packed
+// fp16 Horner.  Max relative error 1.9e-3 including the fp16 rounding of every step (bf16 quantisation alone is
+// 3.9e-3), no range reduction needed.  Takes load off the XU (MUFU) pipe, which bounds the attention kernel.
+__device__ __forceinline__ uint32_t exp2_poly_f16x2(uint32_t xw) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xw);
+  const __half2 c4 = __float2half2_rn(0.009136f), c3 = __float2half2_rn(0.05879032f), c2 = __float2half2_rn(0.24183387f),
+                c1 = __float2half2_rn(0.69174517f), c0 = __float2half2_rn(0.99957738f);
+  __half2 r = __hfma2(c4, x, c3);
+  r = __hfma2(r, x, c2);
+  r = __hfma2(r, x, c1);
+  r = __hfma2(r, x, c0);
+  return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

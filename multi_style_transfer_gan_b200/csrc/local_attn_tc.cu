@@ -23,7 +23,7 @@ constexpr int LT_THREADS = 128;
 constexpr int LT_WARPS = 4;
 constexpr int P16 = 16;
 
-template <int C>
+template <int C, bool POLY>
 __global__ void __launch_bounds__(LT_THREADS, (C == 64 ? 8 : C == 128 ? 4 : 3))
 local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, int W,
                          __nv_bfloat16* __restrict__ out) {
@@ -92,10 +92,16 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
       const bool act = part * 8 < C;          // C = 32: only 4 chunks per pixel
       const uint4* qp = reinterpret_cast<const uint4*>(qs + p * PITCH) + part;
       uint4* kp = reinterpret_cast<uint4*>(ks + p * PITCH) + part;
+      uint4* vp = reinterpret_cast<uint4*>(vs + p * PITCH) + part;
       uint4 kv[VPT];
       float sq = 0.f, sk = 0.f;
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
+        if (act) {                              // v: bf16 -> fp16 in place (exact unless |v| > 65504 or subnormal)
+          const uint4 vv = vp[8 * v];
+          vp[8 * v] = make_uint4(pack_f16x2(bf_lo(vv.x), bf_hi(vv.x)), pack_f16x2(bf_lo(vv.y), bf_hi(vv.y)),
+                                 pack_f16x2(bf_lo(vv.z), bf_hi(vv.z)), pack_f16x2(bf_lo(vv.w), bf_hi(vv.w)));
+        }
         const uint4 qv = act ? qp[8 * v] : make_uint4(0, 0, 0, 0);
         kv[v] = act ? kp[8 * v] : make_uint4(0, 0, 0, 0);
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv[v].x, kv[v].y, kv[v].z, kv[v].w};
@@ -146,24 +152,33 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
       // so the second GEMM is computed transposed: O^T[pixel][i] = sum_j V^T[pixel][j] P^T[j][i], which
       // puts channel pairs in one thread (4-byte conflict-free stores into the [pixel][channel] tile),
       // and an all-ones A operand yields the softmax row sums in the same column layout for free.
+      // P is formed in fp16 (the PV product runs as an f16 mma; v was converted in the staging pass): every other
+      // column tile takes its exponentials on the FMA pipe (packed polynomial) instead of the XU pipe, which ncu
+      // showed to be the busiest unit of this kernel (58 %).
       uint32_t pk[C / 8][2];
 #pragma unroll
       for (int nt = 0; nt < C / 8; ++nt) {
-        pk[nt][0] = ex2_bf16x2(pack_bf16x2(acc[nt][0], acc[nt][1]));
-        pk[nt][1] = ex2_bf16x2(pack_bf16x2(acc[nt][2], acc[nt][3]));
+        const uint32_t x0 = pack_f16x2(acc[nt][0], acc[nt][1]), x1 = pack_f16x2(acc[nt][2], acc[nt][3]);
+        if ((nt & 1) && POLY) {
+          pk[nt][0] = exp2_poly_f16x2(x0);
+          pk[nt][1] = exp2_poly_f16x2(x1);
+        } else {
+          pk[nt][0] = ex2_f16x2(x0);
+          pk[nt][1] = ex2_f16x2(x1);
+        }
       }
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float rsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
+      const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};     // fp16 1.0
 #pragma unroll
       for (int ks16 = 0; ks16 < C / 16; ++ks16) {
         uint32_t va[4];
         // A = V^T stored [pixel][channel] = [m][k]: (p 0-7, j 16ks..), (p 8-15, j 16ks..), (p 0-7, +8), (p 8-15, +8)
         ldsm_x4(vs_a + (r8 + 8 * (mi & 1)) * PITCH + (16 * ks16 + 8 * (mi >> 1)) * 2, va);
-        mma_bf16(o[0], va, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
-        mma_bf16(o[1], va, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
-        mma_bf16(rsum[0], ones, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
-        mma_bf16(rsum[1], ones, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
+        mma_f16(o[0], va, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
+        mma_f16(o[1], va, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
+        mma_f16(rsum[0], ones, pk[2 * ks16][0], pk[2 * ks16 + 1][0]);
+        mma_f16(rsum[1], ones, pk[2 * ks16][1], pk[2 * ks16 + 1][1]);
       }
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -343,18 +358,24 @@ int launch_warp(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* ou
   return check_launch("local_attn_fwd_warp_kernel");
 }
 
-template <int C>
-int launch(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* out, cudaStream_t st) {
+template <int C, bool POLY>
+int launch_impl(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* out, cudaStream_t st) {
   constexpr int PITCH = 2 * C + 16;
   const size_t smem = (size_t)(2 * 3 + 1) * P16 * PITCH;
-  cudaError_t e = cudaFuncSetAttribute(local_attn_fwd_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(local_attn_fwd_tc_kernel<C, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "local_attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const long long nwin = (long long)N * (H / 4) * (W / 4);
   const int per_sm = C >= 256 ? 3 : (C >= 128 ? 4 : 8);   // resident CTAs per SM (smem / register limits)
   long long grid = (long long)per_sm * sm_count();
   if (grid > nwin) grid = nwin;
-  local_attn_fwd_tc_kernel<C><<<(unsigned)grid, LT_THREADS, smem, st>>>(qkv, N, H, W, out);
+  local_attn_fwd_tc_kernel<C, POLY><<<(unsigned)grid, LT_THREADS, smem, st>>>(qkv, N, H, W, out);
   return check_launch("local_attn_fwd_tc_kernel");
+}
+template <int C>
+int launch(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* out, cudaStream_t st) {
+  // MSG_LA_POLY=0: every exponential on the XU pipe (for A/B measurements of the polynomial split)
+  static const bool poly = [] { const char* e = getenv("MSG_LA_POLY"); return !(e && e[0] == '0'); }();
+  return poly ? launch_impl<C, true>(qkv, N, H, W, out, st) : launch_impl<C, false>(qkv, N, H, W, out, st);
 }
 
 }  // namespace
