@@ -92,6 +92,10 @@ typedef struct {
  * in_stats fp64 [N][Ci_total][2] raw sums of the input plane (only with MSG_CONV_IN_NORM). */
 int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                double* stats, const double* in_stats, void* stream);
+/* Which engine msg_conv2d would take for this descriptor / these pointers, without launching anything:
+ * 2 = persistent TMA + tcgen05 kernel, 1 = cp.async gather + tcgen05 kernel, 0 = SIMT engine, < 0 = MSG_ERR_*.
+ * (Callers use it to decide whether fusing the input InstanceNorm into a 1x1 conv is profitable.) */
+int msg_conv2d_path(const msg_conv_desc* d, const void* x, const void* w, const void* y);
 
 /* ---------------------------------------------------------------------------------------------
  * "Row-slab" convolution (bf16, W % 8 == 0): stride-1, same-size convs with small N, several taps

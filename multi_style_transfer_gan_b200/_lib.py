@@ -61,6 +61,7 @@ SIGNATURES = {
     "msg_check_device": [],
     "msg_sm_count": [],
     "msg_conv2d": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
+    "msg_conv2d_path": [ctypes.POINTER(ConvDesc), _P, _P, _P],
     "msg_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
     "msg_conv_slab": [ctypes.POINTER(SlabDesc), _P, _P, _P, _P, _P, _P],
     "msg_conv_shift": [ctypes.POINTER(ShiftDesc), _P, _P, _P, _P, _P, _P],

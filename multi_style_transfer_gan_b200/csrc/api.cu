@@ -47,7 +47,7 @@ int conv2d_simt(const msg_conv_desc* d, const void* x, const void* w, const floa
                 double* stats, const double* in_stats, cudaStream_t st);
 bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
 int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-               double* stats, cudaStream_t st);
+               double* stats, const double* in_stats, cudaStream_t st);
 bool conv2d_tc_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
 int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
               double* stats, const double* in_stats, cudaStream_t st);
@@ -60,7 +60,7 @@ int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const 
   MSG_REQUIRE(!(d->flags & MSG_CONV_IN_NORM) || in_stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_IN_NORM without in_stats");
   if (!(d->flags & MSG_CONV_FORCE_SIMT)) {
     if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_tma_supported(d, x, w, y))
-      return conv2d_tma(d, x, w, bias, y, stats, st);            // persistent TMA + tcgen05 kernel
+      return conv2d_tma(d, x, w, bias, y, stats, in_stats, st);            // persistent TMA + tcgen05 kernel
     if (conv2d_tc_supported(d, x, w, y))
       return conv2d_tc(d, x, w, bias, y, stats, in_stats, st);   // cp.async gather + tcgen05 kernel
   }
@@ -82,6 +82,17 @@ extern "C" int msg_check_device(void) {
   MSG_REQUIRE(d.major == 10, MSG_ERR_ARCH,
               "msg_b200 kernels are built for sm_100a only; device is sm_%d%d (no fallback)", d.major, d.minor);
   return MSG_OK;
+}
+
+extern "C" int msg_conv2d_path(const msg_conv_desc* d, const void* x, const void* w, const void* y) {
+  MSG_REQUIRE(d != nullptr, MSG_ERR_SHAPE, "conv: null descriptor");
+  int rc = conv_validate(d);
+  if (rc) return rc;
+  if (!(d->flags & MSG_CONV_FORCE_SIMT)) {
+    if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_tma_supported(d, x, w, y)) return 2;
+    if (conv2d_tc_supported(d, x, w, y)) return 1;
+  }
+  return 0;
 }
 
 extern "C" int msg_conv2d(const msg_conv_desc* d, const void* x, const void* w, const float* bias,

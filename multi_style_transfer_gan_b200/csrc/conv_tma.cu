@@ -33,6 +33,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NTHREADS = 320;          // producer + MMA warp + up to two epilogue groups of four warps
+constexpr int NTHREADS_XF = 448;       // ... + four transform warps (fused input InstanceNorm)
 constexpr int EPI_FIXED = 16384 + 4 * 1056 * 4;  // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][33]
 constexpr int STAGE_PITCH = 128 + 16;   // manual flush: 64 bf16 columns per row + 16 B skew
 constexpr int STAGE_BYTES = 2 * BM * 128;   // two [128 rows x 64 cols] bf16 TMA-store buffers (SW128)
@@ -137,6 +138,8 @@ struct TmaParams {
   void* y;
   double* stats;
   int BN, n_tiles, m_tiles, stages, tmem_cols;
+  const double* in_stats;   // MSG_CONV_IN_NORM: raw plane sums [N][Ci_total][2] of the INPUT tensor
+  int xform;          // 1: four transform warps apply InstanceNorm + activation to every A tile in smem (1x1 convs)
   int b_resident;     // 1: all nkb weight tiles of the (single) N tile stay in smem for the whole kernel
   int epi_groups;     // 1: warps 2-5 drain both accumulator buffers; 2: warps 2-5 own buffer 0, warps 6-9 buffer 1
   int Wt, R;            // M tile = R rows x Wt pixels
@@ -145,7 +148,8 @@ struct TmaParams {
   int tstore;           // output rows of a tile are 128 consecutive pixels: full 64-column groups go out by TMA
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool XFORM>
+__global__ void __launch_bounds__(XFORM ? NTHREADS_XF : NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapC, const TmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -160,23 +164,26 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t sStage = sB + (p.b_resident ? p.nkb : S) * b_bytes;   // epilogue staging, 1024-byte aligned
   const uint32_t sRed = sStage + p.epi_groups * STAGE_BYTES;              // per-warp column sums / transpose scratch
   const uint32_t sBias = sRed + p.epi_groups * EPI_FIXED;                 // bias staged once per CTA (<= 1024 floats)
-  const uint32_t sBar = sBias + 4096;                       // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t sXfTab = sBias + 4096;                     // fused input norm: scale[512], shift[512] of the current image
+  const uint32_t sBar = sXfTab + 4096;                      // full[S], empty[S], xf[S], tfull[2], tempty[2], wres, tmem slot
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
   float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
+  float* xf_tab = reinterpret_cast<float*>(gen + (sXfTab - base));
   const bool bias_in_smem = p.bias != nullptr && d.Cout <= 1024;
   if (bias_in_smem)
     for (int i = tid; i < d.Cout; i += (int)blockDim.x) sbias[i] = p.bias[i];
-  const uint32_t wres_bar = sBar + 8u * (2 * S + 4);        // "resident weights have landed"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
+  const uint32_t wres_bar = sBar + 8u * (3 * S + 4);        // "resident weights have landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (3 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
-  auto tfull_bar = [&](int b) { return sBar + 8u * (2 * S + b); };
-  auto tempty_bar = [&](int b) { return sBar + 8u * (2 * S + 2 + b); };
+  auto xf_bar = [&](int s) { return sBar + 8u * (2 * S + s); };          // "A tile of stage s has been normalised"
+  auto tfull_bar = [&](int b) { return sBar + 8u * (3 * S + b); };
+  auto tempty_bar = [&](int b) { return sBar + 8u * (3 * S + 2 + b); };
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(xf_bar(s), 4); }
       for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
       mbar_init(wres_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -250,7 +257,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(XFORM ? xf_bar(s) : full_bar(s), ph);
           tc_fence_after();
           const uint64_t da = desc_hi | (uint64_t)(a_base + (uint32_t)s * a_step);
           const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)(p.b_resident ? kb : s) * b_step);
@@ -268,7 +275,67 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (((warp - 2) >> 2) < p.epi_groups) {
+  } else if (XFORM && warp >= 2 + 4 * p.epi_groups) {
+    // ===================================== fused input InstanceNorm (four transform warps) ==========
+    // 1x1 convs only: the A tile is 128 consecutive pixels of ONE image x 64 channels, 128B-swizzled by TMA.
+    // Each landed stage is rewritten in place as act((x - mean) * rstd) with the apply kernel's exact arithmetic
+    // (fmaf(x, scale, shift), bf16 round-to-nearest), so the fused conv is bit-identical to IN-apply + conv while
+    // the normalised tensor never exists in HBM.  Thread t owns physical 16-byte chunk (t & 7) of rows (t >> 3) + 16 i:
+    // a warp touches 512 contiguous bytes per access (conflict-free) and, because the swizzle only uses row & 7, the
+    // LOGICAL channel chunk of a thread is the same for all its rows -- its 8 scales / shifts live in registers.
+    const int xt = tid - 32 * (2 + 4 * p.epi_groups);           // 0..127
+    const int pchunk = xt & 7, rbase = xt >> 3;
+    const int lchunk = pchunk ^ (rbase & 7);
+    const int hw = d.Hg * d.Wg;
+    const double inv_hw = 1.0 / (double)hw;
+    int cur_img = -1, cur_cb = -1;
+    float sc[8], sh[8];
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int mt = t / p.n_tiles;
+      const int img = (int)(((long long)mt * BM) / hw);
+      if (img != cur_img) {                                      // new image: rebuild the per-channel table
+        asm volatile("bar.sync 2, 128;" ::: "memory");           // everyone is done reading the old table
+        for (int ci = xt; ci < d.Cin; ci += 128) {
+          const double* st = p.in_stats + ((size_t)img * d.Ci_total + d.ci_off + ci) * 2;
+          float mean, rstd;
+          finalize_stats(st[0], st[1], inv_hw, mean, rstd);
+          xf_tab[ci] = rstd;
+          xf_tab[512 + ci] = 0.f - mean * rstd;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        cur_img = img; cur_cb = -1;
+      }
+      for (int kb = 0; kb < p.nkb; ++kb) {                       // 1x1 conv: K block kb = channel block kb
+        if (kb != cur_cb) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sc[e] = xf_tab[kb * 64 + lchunk * 8 + e]; sh[e] = xf_tab[512 + kb * 64 + lchunk * 8 + e]; }
+          cur_cb = kb;
+        }
+        mbar_wait(full_bar(s), ph);
+        uint8_t* tile = gen + (sA - base) + s * A_BYTES + rbase * 128 + pchunk * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4* ptr = reinterpret_cast<uint4*>(tile + i * (16 * 128));
+          float v[8];
+          unpack8(*ptr, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float o = fmaf(v[e], sc[e], sh[e]);
+            if (d.in_act == MSG_ACT_RELU) o = fmaxf(o, 0.f);
+            else if (d.in_act == MSG_ACT_LRELU) o = o > 0.f ? o : 0.2f * o;
+            v[e] = o;
+          }
+          *ptr = pack8(v);
+        }
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xf_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 2 && ((warp - 2) >> 2) < p.epi_groups) {
     // ===================================== epilogue (warps 2-5, and 6-9 with two groups) ===========
     // The epilogue of a 128 x BN tile is a single warp's instruction stream per 32 rows (~550 instructions per 64
     // columns with bias + statistics): with one warp per scheduler it is latency-bound and, for the 1x1 convs
@@ -517,7 +584,11 @@ int pick_bn(int Cout) {
 
 bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y) {
   if (d->dtype != MSG_BF16) return false;
-  if (d->flags & MSG_CONV_IN_NORM) return false;
+  if (d->flags & MSG_CONV_IN_NORM) {     // fused input InstanceNorm: 1x1 stride-1 convs whose tile lies in one image
+    if (d->KH != 1 || d->KW != 1 || d->in_stride != 1 || d->pad_h || d->pad_w || d->Cin > 512) return false;
+    if (((long long)d->Hg * d->Wg) % BM) return false;
+    if (d->in_act != MSG_ACT_NONE && d->in_act != MSG_ACT_RELU && d->in_act != MSG_ACT_LRELU) return false;
+  }
   if (d->Cin % 64 || (d->Ci_total & 7) || (d->ci_off & 7)) return false;
   if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
   if (!(d->flags & MSG_CONV_OUT_NCHW_F32) && ((uintptr_t)y & 15)) return false;
@@ -530,13 +601,14 @@ bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, 
 }
 
 int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-               double* stats, cudaStream_t st) {
+               double* stats, const double* in_stats, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled unavailable");
   Tiling tl;
   MSG_REQUIRE(pick_tiling(d, &tl), MSG_ERR_UNSUPPORTED, "conv_tma: unsupported plane geometry");
   TmaParams p;
-  p.d = *d; p.bias = bias; p.y = y; p.stats = stats;
+  p.d = *d; p.bias = bias; p.y = y; p.stats = stats; p.in_stats = in_stats;
+  p.xform = (d->flags & MSG_CONV_IN_NORM) ? 1 : 0;
   p.BN = pick_bn(d->Cout);
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
   p.m_tiles = (int)((long long)d->N * d->Hg * d->Wg / BM);
@@ -553,13 +625,13 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   // two epilogue groups when the extra staging / scratch (57 KB) still leaves >= 3 pipeline stages
   static const int env_groups = [] { const char* e = getenv("MSG_TMA_EPI_GROUPS"); return e ? atoi(e) : 0; }();
   {
-    const int st2 = (220 * 1024 - bres_bytes - (2 * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024)) / stage_bytes;
+    const int st2 = (220 * 1024 - bres_bytes - (2 * (STAGE_BYTES + EPI_FIXED) + 4096 + 4096 + 320 + 1024)) / stage_bytes;
     // K-heavy tiles (many K blocks per tile) are L2->SM-bound and want the deep ring; the 1x1 convs (<= 4 K blocks
     // per tile) are epilogue-bound and fine with 2 stages
     p.epi_groups = (st2 >= 5 || (st2 >= 2 && p.nkb <= 4)) ? 2 : 1;
   }
   if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
-  const int fixed = p.epi_groups * (STAGE_BYTES + EPI_FIXED) + 4096 + 8 * 16 + 64 + 1024 + bres_bytes;
+  const int fixed = p.epi_groups * (STAGE_BYTES + EPI_FIXED) + 4096 + 4096 + 320 + 1024 + bres_bytes;
   static const bool env_tstore = [] { const char* e = getenv("MSG_TMA_STORE"); return !(e && e[0] == '0'); }();
   p.tstore = (env_tstore && !(d->flags & (MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM)) && d->out_stride == 1 && d->out_off_h == 0 &&
               d->out_off_w == 0 && d->Ho == d->Hg && d->Wo == d->Wg && ((d->Co_total | d->co_off) & 7) == 0 &&
@@ -606,14 +678,16 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   int grid = sm_count();
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
-  conv_tma_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(mapA, mapB, mapC, p);
+  if (p.xform) conv_tma_kernel<true><<<grid, 64 + 128 * p.epi_groups + 128, smem, st>>>(mapA, mapB, mapC, p);
+  else conv_tma_kernel<false><<<grid, 64 + 128 * p.epi_groups, smem, st>>>(mapA, mapB, mapC, p);
   return check_launch("conv_tma_kernel");
 }
 

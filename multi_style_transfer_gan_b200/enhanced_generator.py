@@ -161,7 +161,7 @@ class _GeneratorFn(torch.autograd.Function):
     def forward(ctx, model, dtype, keys, x, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:])
+        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         a, s_enc = eng.encode(P, x, dtype, save)
         y, s_dec = eng.decode(P, a, dtype, save)
@@ -189,7 +189,7 @@ class _EncoderFn(torch.autograd.Function):
     def forward(ctx, model, dtype, keys, x, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:])
+        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         a, s_enc = eng.encode(P, x, dtype, save)
         if need:
@@ -212,7 +212,7 @@ class _DecoderFn(torch.autograd.Function):
     def forward(ctx, model, dtype, keys, a, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:])
+        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         y, s_dec = eng.decode(P, a.contiguous().to(dtype), dtype, save)
         if need:
@@ -298,6 +298,9 @@ class EnhancedGenerator(nn.Module):
         dtype = _resolve_dtype(self.precision)
         keys, params = self._kernel_params()
         xin = x if x.dtype == torch.float32 else x.float()
+        # autograd.Function.forward always runs with grad mode off and ctx.needs_input_grad ignores no_grad, so the
+        # caller's grad mode is recorded here: under no_grad nothing is saved and the inference schedule is used
+        self._grad_on = torch.is_grad_enabled()
         if self._blocks_are_identity():
             # style_encoder output is only consumed by the (identity) blocks: dead, skipped
             return _GeneratorFn.apply(self, dtype, keys, xin.contiguous(), *params)
@@ -351,8 +354,8 @@ class _DiscriminatorFn(torch.autograd.Function):
         eng = model._engine
         P = dict(zip(keys, params))
         P.update(model._buffers_dict())
-        need_dx = ctx.needs_input_grad[4]
-        need_dw = any(ctx.needs_input_grad[5:])
+        need_dx = model._grad_on and ctx.needs_input_grad[4]
+        need_dw = model._grad_on and any(ctx.needs_input_grad[5:])
         save = need_dx or need_dw
         ctx.set_materialize_grads(False)   # unused head (score or struct) -> None, not zeros
         score, struct, saved = eng.forward(P, x, dtype, training, save)
@@ -410,5 +413,6 @@ class EnhancedDiscriminator(nn.Module):
         dtype = _resolve_dtype(self.precision)
         keys, params = zip(*self.named_parameters())
         xin = x if x.dtype == torch.float32 else x.float()
+        self._grad_on = torch.is_grad_enabled()    # see EnhancedGenerator.forward
         score, struct = _DiscriminatorFn.apply(self, dtype, self.training, tuple(keys), xin.contiguous(), *params)
         return score.squeeze(), struct      # .squeeze(): 0-dim when B == 1 (:275)

@@ -59,6 +59,7 @@ class GeneratorEngine:
         self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
         self._msb64_prog = slab.msb64_shift_program()
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
+        self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
 
     def _versions(self, params, names):
         return tuple((params[n].data_ptr(), params[n]._version) for n in names)
@@ -122,8 +123,15 @@ class GeneratorEngine:
         dev = a_in.device
         st0 = ops.new_stats(N, C, dev)
         y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
-        a0 = ops.instnorm_apply(y0, st0, ACT_RELU, out=None if keep else y0)
-        qkv = g[f"{s}.3.qkv"].forward(a0, self._packed(P, f"{s}.3.qkv", "fwd", dtype), self._bias(P, f"{s}.3.qkv"))
+        wq = self._packed(P, f"{s}.3.qkv", "fwd", dtype)
+        if not keep and self.fuse_in_norm and g[f"{s}.3.qkv"].fused_in_norm_ok(y0, wq):
+            # inference: ReLU(IN(y0)) has ONE consumer, the 1x1 qkv conv (LocalAttention has no residual), so the
+            # conv normalises its A tiles in shared memory and the normalised tensor never exists in HBM
+            a0 = None
+            qkv = g[f"{s}.3.qkv"].forward(y0, wq, self._bias(P, f"{s}.3.qkv"), in_stats=st0, in_act=ACT_RELU)
+        else:
+            a0 = ops.instnorm_apply(y0, st0, ACT_RELU, out=None if keep else y0)
+            qkv = g[f"{s}.3.qkv"].forward(a0, wq, self._bias(P, f"{s}.3.qkv"))
         att = ops.local_attn_fwd(qkv)
         if not keep:
             del y0, a0, qkv
@@ -149,10 +157,15 @@ class GeneratorEngine:
             for i in range(1, 5):
                 n = f"{s}.4.branch{i}.0"
                 g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
-        bn = ops.instnorm_apply(b, stb, ACT_RELU, out=None if keep else b)
         stf = ops.new_stats(N, C, dev)
         n = f"{s}.4.fusion.0"
-        f = g[n].forward(bn, self._packed(P, n, "fwd", dtype), self._bias(P, n), stats=stf)
+        wf = self._packed(P, n, "fwd", dtype)
+        if not keep and self.fuse_in_norm and g[n].fused_in_norm_ok(b, wf):
+            bn = None       # ReLU(IN(branches)) is consumed only by the 1x1 fusion conv: normalised on the fly
+            f = g[n].forward(b, wf, self._bias(P, n), stats=stf, in_stats=stb, in_act=ACT_RELU)
+        else:
+            bn = ops.instnorm_apply(b, stb, ACT_RELU, out=None if keep else b)
+            f = g[n].forward(bn, wf, self._bias(P, n), stats=stf)
         a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1, out=None if keep else f)
         if not keep:
             return a2, None

@@ -101,6 +101,25 @@ class ConvGeom:
             return pack_weight(w, PACK_CONVT_PHASES, dtype, sigma)  # conv weight read as convT weight
         return pack_weight(w, PACK_DGRAD_S1, dtype, sigma)
 
+    def fused_in_norm_ok(self, x, wp):
+        """True when msg_conv2d would run this conv WITH a fused input InstanceNorm on the TMA + tcgen05 kernel
+        (1x1 stride-1 convs, bf16, Cin % 64 == 0, tiles inside one image); otherwise the caller keeps the separate
+        IN-apply pass (the only other engine with a fused input norm is the SIMT parity engine)."""
+        if self.kind != "conv" or self.k != 1 or self.stride != 1:
+            return False
+        N, Hi, Wi, Ci_total = x.shape
+        key = (N, Hi, Wi, Ci_total, x.dtype)
+        hit = self._fuse_cache.get(key) if hasattr(self, "_fuse_cache") else None
+        if hit is None:
+            if not hasattr(self, "_fuse_cache"):
+                self._fuse_cache = {}
+            d = make_desc(_dt(x), N, Hi, Wi, Ci_total, 0, self.Cin, Hi, Wi, self.Cout, 0, self.Cout, Hi, Wi, 1, 1, 1, 0, 0,
+                          1, 1, 0, 0, ACT_NONE, CONV_IN_NORM, ACT_RELU)
+            # pointers only matter for their alignment: fresh torch allocations are 256-byte aligned like x / wp
+            hit = _lib.load().msg_conv2d_path(ctypes.byref(d), _p(x), _p(wp), _p(x)) == 2
+            self._fuse_cache[key] = hit
+        return hit
+
     # ---- launches
     def forward(self, x, wp, bias, out=None, co_off=0, stats=None, act=ACT_NONE, in_stats=None,
                 in_act=ACT_NONE, ci_off=0, nchw_out=None, extra_flags=0):

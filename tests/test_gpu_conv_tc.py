@@ -214,3 +214,34 @@ def test_wgrad_tc_vs_simt_and_torch(case):
     assert_parity(dw_si, w.grad, 1e-2, "simt wgrad vs torch")
     assert_parity(dw_tc, w.grad, 1e-2, "tcgen05 wgrad vs torch")
     assert_parity(dw_tc, dw_si, 2e-3, "tcgen05 wgrad vs simt")
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,N,act", [(64, 192, 64, 64, 3, "relu"), (128, 384, 32, 32, 2, "relu"),
+                                                (256, 768, 16, 32, 2, "relu"), (64, 64, 16, 128, 5, "lrelu"),
+                                                (128, 128, 8, 64, 2, "none")])
+def test_fused_input_instnorm_1x1_is_bit_identical(Cin, Cout, H, W, N, act):
+    """conv_tma's transform warps (MSG_CONV_IN_NORM on a 1x1 conv) normalise every A tile in shared memory with the
+    apply kernel's arithmetic: the result must equal IN-apply followed by the plain conv BIT FOR BIT, including
+    the output statistics, for tiles of several images per CTA, several channel blocks and several N tiles."""
+    from multi_style_transfer_gan_b200 import ops
+    torch.manual_seed(21)
+    A = {"relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU, "none": ops.ACT_NONE}[act]
+    x = (torch.randn(N, H, W, Cin, device=DEV) * 2 + 0.5).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 1, 1, device=DEV) * 0.1
+    bias = torch.randn(Cout, device=DEV)
+    g = ops.ConvGeom("conv", Cin, Cout, 1, 1, 0, 1)
+    wp = g.pack_fwd(w, torch.bfloat16)
+    assert g.fused_in_norm_ok(x, wp), "this geometry should take the TMA kernel with a fused input norm"
+    st = ops.new_stats(N, Cin, DEV)
+    ops.instnorm_stats(x, st)
+    xn = ops.instnorm_apply(x, st, A)
+    s_ref, s_fused = ops.new_stats(N, Cout, DEV), ops.new_stats(N, Cout, DEV)
+    ref = g.forward(xn, wp, bias, stats=s_ref)
+    fused = g.forward(x, wp, bias, stats=s_fused, in_stats=st, in_act=A)
+    assert torch.equal(ref, fused)
+    assert torch.allclose(s_ref, s_fused, rtol=1e-12, atol=1e-9)
+    # and it is a real InstanceNorm: compare with torch on the same bf16 input
+    t = F.instance_norm(nchw(x), eps=1e-5)
+    t = {"relu": torch.relu, "lrelu": lambda v: F.leaky_relu(v, 0.2), "none": lambda v: v}[act](t)
+    t = F.conv2d(t.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias)
+    assert_parity(nchw(fused), t, 2e-2, "fused IN + 1x1 conv vs torch")

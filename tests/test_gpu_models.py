@@ -317,3 +317,21 @@ def test_config5_highres_four_style_blend_properties():
     st(x.cpu().pin_memory(), w, out_uint8=True, out=u8)
     torch.cuda.synchronize()
     assert (u8.int() - R.to_uint8_image(y.cpu()).int()).abs().max() <= 1
+
+
+def test_fused_input_norm_does_not_change_the_generator():
+    """Inference fuses ReLU(IN(.)) into its only consumer (the 1x1 qkv / fusion convs) where the TMA kernel supports
+    it; the output must be identical to the unfused schedule."""
+    from multi_style_transfer_gan_b200.enhanced_generator import EnhancedGenerator
+    torch.manual_seed(0)
+    g = EnhancedGenerator(channels=64, num_transformer_blocks=3).to(DEV).eval()
+    g.set_precision("bf16")
+    x = torch.rand(2, 3, 128, 128, device=DEV) * 2 - 1
+    eng = g._engine if hasattr(g, "_engine") else g.engine
+    with torch.no_grad():
+        assert eng.fuse_in_norm
+        y1 = g(x)
+        eng.fuse_in_norm = False
+        y0 = g(x)
+        eng.fuse_in_norm = True
+    assert torch.equal(y0, y1)
