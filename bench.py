@@ -236,9 +236,20 @@ def run_ours(args):
                                 "launches_per_step": conv_launches, "ms_per_step": conv_ms}
         in_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in ("msg_instnorm_apply", "msg_instnorm_stats")) / args.steps
         if in_ms > 0:
-            gbs = 3 * B * IN_BYTES_512_BF16 * scale / (in_ms * 1e-3) / 1e9
+            in_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in ("msg_instnorm_apply", "msg_instnorm_stats")) // args.steps
+            per_fwd = in_launches // (3 * max(1, (B + args.micro_batch - 1) // args.micro_batch))
+            if per_fwd <= 5:
+                # 8 of the 13 IN applies of a forward are fused into their 1x1 consumers (no HBM pass at all); the
+                # stand-alone launches left are the initial IN (1 read + 1 write of [c, H, W]) and the four
+                # MultiScaleBlock outputs (read + residual read + write): bytes of exactly those launches (bf16)
+                c = args.channels
+                elems = c * H * W * 2 + 3 * (2 * (2 * c) * (H // 2) * (W // 2) + (4 * c) * (H // 4) * (W // 4) + c * H * W)
+                in_bytes, note = elems * 2, "5 stand-alone apply launches per forward (8 fused into 1x1 convs)"
+            else:
+                in_bytes, note = IN_BYTES_512_BF16 * scale, "13 apply launches per forward, 1 read + 1 write each (SURVEY 8d)"
+            gbs = 3 * B * in_bytes / (in_ms * 1e-3) / 1e9
             line["roofline_instnorm"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                         "frac": gbs / pk["hbm_gbs"], "ms_per_step": in_ms}
+                                         "frac": gbs / pk["hbm_gbs"], "ms_per_step": in_ms, "bytes": note}
         line["breakdown_ms_per_step"] = {k: round(v["ms"] / args.steps, 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
