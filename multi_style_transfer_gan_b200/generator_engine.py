@@ -55,6 +55,7 @@ class GeneratorEngine:
         # row-slab programs (bf16 path, widths that are multiples of 64): fused MSB branches, 7x7 convs
         self.use_slab = True
         self._msb_prog = {C: slab.msb_program(C) for C in set(self.width.values()) if C % 64 == 0}
+        self._msb_dprog = {C: slab.msb_dgrad_program(C) for C in set(self.width.values()) if C % 64 == 0}
         self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
         self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
         self._msb64_prog = slab.msb64_shift_program()
@@ -258,10 +259,19 @@ class GeneratorEngine:
         df = ops.instnorm_bwd(sv["f"], sv["stf"], da2, ACT_RELU)
         dbn = self._conv_bwd(P, G, f"{s}.4.fusion.0", sv["bn"], df, dtype)
         db = ops.instnorm_bwd(sv["b"], sv["stb"], dbn, ACT_RELU)
-        da1 = da2.clone()  # residual path: d(a1) starts as d(a2)
-        for i in range(1, 5):
-            self._conv_bwd(P, G, f"{s}.4.branch{i}.0", sv["a1"], db, dtype, dy_c_off=(i - 1) * (C // 4),
-                           dx_out=da1, accumulate=True)
+        if self.use_slab and dtype == torch.bfloat16 and C in self._msb_dprog and db.shape[2] % 8 == 0:
+            # data gradient of the four branches: one row-slab launch (N = C per tap) + the residual add
+            wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
+            dprog = self._msb_dprog[C]
+            wsl = self._slab_cached(P, (s, "msb_dw"), wn, lambda: slab.msb_dgrad_weight_slab(dprog, [P[k].detach() for k in wn]))
+            da1 = ops.add(slab.conv_slab(dprog, db, wsl, None), da2)
+            for i in range(1, 5):
+                self._conv_bwd(P, G, f"{s}.4.branch{i}.0", sv["a1"], db, dtype, dy_c_off=(i - 1) * (C // 4), need_dx=False)
+        else:
+            da1 = da2.clone()  # residual path: d(a1) starts as d(a2)
+            for i in range(1, 5):
+                self._conv_bwd(P, G, f"{s}.4.branch{i}.0", sv["a1"], db, dtype, dy_c_off=(i - 1) * (C // 4),
+                               dx_out=da1, accumulate=True)
         datt = self._conv_bwd(P, G, f"{s}.3.proj", sv["att"], da1, dtype)
         dqkv = ops.local_attn_bwd(sv["qkv"], datt)
         da0 = self._conv_bwd(P, G, f"{s}.3.qkv", sv["a0"], dqkv, dtype)

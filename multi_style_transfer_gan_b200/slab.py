@@ -69,6 +69,47 @@ def msb_weight_slab(prog, weights, dtype=torch.bfloat16):
     return torch.cat(rows, 0).to(dtype).contiguous()
 
 
+def msb_dgrad_program(C):
+    """Data gradient of the four fused branches in ONE launch: the input is the concatenated branch gradient
+    dB [N,H,W,C] (branch b = channels [bq, (b+1)q)), the output d(a1) [N,H,W,C] = sum over branches and taps of
+    dB_b[y - dy][x - sx] W_b[:, :, kh, kw]^T.  Every tap is an N = C MMA group on the 64-channel block that holds
+    the branch's slice (weight columns of other branches in that block are zero), instead of four small-Cin
+    convs on the gather kernel with an accumulate pass each."""
+    q = C // 4
+    branches = [(1, 1), (3, 1), (3, 2), (3, 4)]
+    max_taps = max(1, (64 * 1024) // (C * 128))
+    kblocks = []
+    for dy in (-4, -2, -1, 0, 1, 2, 4):
+        for cb in range(C // 64):
+            taps = []
+            for b, (k, dil) in enumerate(branches):
+                if (b * q) // 64 != cb:
+                    continue
+                for kh in range(k):
+                    if -(kh - k // 2) * dil != dy:
+                        continue
+                    for kw in range(k):
+                        taps.append((-(kw - k // 2) * dil, 0, 0, (b, kh, kw, cb)))
+            for i in range(0, len(taps), max_taps):
+                kblocks.append((dy, cb, taps[i:i + max_taps]))
+    return SlabProgram(C, C, C, C, 4, False, kblocks)
+
+
+def msb_dgrad_weight_slab(prog, weights, dtype=torch.bfloat16):
+    """weights: [w_branch1 [q,C,1,1], w_branch2..4 [q,C,3,3]] fp32 -> bf16 [n_taps*C, 64]: tile row = input channel ci
+    of the forward conv (= output channel of the dgrad), column kk = channel cb*64 + kk of dB."""
+    C = prog.Cin
+    q = C // 4
+    rows = []
+    for _, _, taps in prog.kblocks:
+        for _, _, _, (b, kh, kw, cb) in taps:
+            t = torch.zeros(C, 64, device=weights[b].device, dtype=torch.float32)
+            k0 = b * q - cb * 64                           # first column of branch b inside this 64-channel block
+            t[:, k0:k0 + min(q, 64)] = weights[b][:, :, kh, kw].t()[:, :min(q, 64)]
+            rows.append(t)
+    return torch.cat(rows, 0).to(dtype).contiguous()
+
+
 def conv7_out_program(c):
     kblocks = []
     for kh in range(7):

@@ -245,3 +245,21 @@ def test_fused_input_instnorm_1x1_is_bit_identical(Cin, Cout, H, W, N, act):
     t = {"relu": torch.relu, "lrelu": lambda v: F.leaky_relu(v, 0.2), "none": lambda v: v}[act](t)
     t = F.conv2d(t.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias)
     assert_parity(nchw(fused), t, 2e-2, "fused IN + 1x1 conv vs torch")
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 16, 128), (128, 8, 128), (256, 4, 128), (64, 12, 72)])
+def test_slab_msb_dgrad(C, H, W):
+    """Fused data gradient of the four MultiScaleBlock branches (one row-slab launch) against autograd of the four
+    torch convs on the same bf16-rounded operands."""
+    from multi_style_transfer_gan_b200 import slab
+    torch.manual_seed(31)
+    q, N = C // 4, 2
+    ws = [torch.randn(q, C, k, k, device=DEV) * 0.05 for k in (1, 3, 3, 3)]
+    db = torch.randn(N, C, H, W, device=DEV).to(torch.bfloat16)
+    x = torch.zeros(N, C, H, W, device=DEV, requires_grad=True)
+    outs = [F.conv2d(x, w.to(torch.bfloat16).float(), padding=(w.shape[2] // 2) * d, dilation=d)
+            for w, d in zip(ws, (1, 1, 2, 4))]
+    torch.cat(outs, 1).backward(db.float())
+    prog = slab.msb_dgrad_program(C)
+    got = slab.conv_slab(prog, nhwc(db.float()), slab.msb_dgrad_weight_slab(prog, ws), None)
+    assert_parity(nchw(got), x.grad, 1e-2, "fused MSB dgrad")
