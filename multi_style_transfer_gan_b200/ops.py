@@ -240,14 +240,16 @@ def instnorm_apply(x, stats, act=ACT_RELU, residual=None, out=None, gammas=None,
     return out
 
 
-def instnorm_bwd(x, stats, dy, act=ACT_RELU, out=None):
+def instnorm_bwd(x, stats, dy, act=ACT_RELU, out=None, return_scratch=False):
+    """return_scratch: also return the kernel's per-(n, c) reductions [N, C, 2] = (sum g, sum g * xhat) with
+    g = dy * act'(xhat) -- for a BatchNorm (N = 1 view) these are d(beta) and d(gamma)."""
     _dev(x)
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
     scratch = torch.empty((N, C, 2), device=x.device, dtype=torch.float64)
     _lib.call("msg_instnorm_bwd", _dt(x), _p(x), _p(stats), _p(dy), N, H * W, C, act, _p(scratch), _p(out), _stream())
-    return out
+    return (out, scratch) if return_scratch else out
 
 
 # ---- LocalAttention core -------------------------------------------------------------------------

@@ -134,6 +134,28 @@ def main():
     torch.save({"local_attention": la_pack, "multi_scale_block": msb_pack},
                os.path.join(OUT, "blocks_c32.pt"))
 
+    # ---- pretrain.Generator (BatchNorm auto-encoder, pretrain.py:60-97) + the masked-L1 objective (:159-160)
+    import pretrain as pt  # the unmodified reference module (imports cleanly once the stub is installed)
+    Gp = build(pt.Generator, 0, channels=8)
+    init = {k: v.detach().clone() for k, v in Gp.state_dict().items()}
+    real = synth_images(3, 64, 64, seed=21)
+    gm = torch.Generator().manual_seed(22)
+    mask = (torch.rand(3, 1, 64, 64, generator=gm) > 0.3).float()
+    masked = (real * mask).requires_grad_(True)
+    Gp.train()
+    y = Gp(masked)
+    loss = torch.nn.L1Loss()(y * (1 - mask), real * (1 - mask))
+    loss.backward()
+    after = {k: v.detach().clone() for k, v in Gp.state_dict().items() if "running" in k or "num_batches" in k}
+    Gp.eval()
+    with torch.no_grad():
+        y_eval = Gp(masked.detach())
+    torch.save({"init": init, "real": real, "mask": mask, "masked": masked.detach().clone(), "y_train": y.detach(),
+                "loss": loss.detach(), "dx": masked.grad.clone(),
+                "grads": {k: p.grad.clone() for k, p in Gp.named_parameters()},
+                "running_after": after, "y_eval": y_eval, "keys": list(Gp.state_dict().keys())},
+               os.path.join(OUT, "pretrain_c8_64.pt"))
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

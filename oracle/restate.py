@@ -302,6 +302,45 @@ def to_uint8_image(y):
 
 
 # --------------------------------------------------------------------------------------------
+# pretrain.Generator (pretrain.py:60-97): 4x[Conv4x4 s2 (+BN) + LeakyReLU 0.2] -> 4x[ConvT4x4 s2 (+BN) + ReLU], tanh
+# --------------------------------------------------------------------------------------------
+PRETRAIN_ENC = ((0, None), (2, 3), (5, 6), (8, 9))      # (conv index, BatchNorm index) inside `encoder`
+PRETRAIN_DEC = ((0, 1), (3, 4), (6, 7), (9, None))      # (convT index, BatchNorm index) inside `decoder`
+
+
+def pretrain_generator_forward(sd, x, training=True, momentum=0.1, eps=1e-5):
+    """Functional restatement of pretrain.Generator.forward (pretrain.py:93-96) on a state_dict.  In training mode
+    BatchNorm uses batch statistics and the returned dict holds the UPDATED running statistics
+    (torch.nn.BatchNorm2d semantics: biased variance to normalise, unbiased for the running estimate)."""
+    new = {}
+
+    def bn(h, pre):
+        rm, rv = sd[pre + ".running_mean"].clone(), sd[pre + ".running_var"].clone()
+        y = F.batch_norm(h, rm, rv, sd[pre + ".weight"], sd[pre + ".bias"], training, momentum, eps)
+        if training:
+            new[pre + ".running_mean"], new[pre + ".running_var"] = rm, rv
+            new[pre + ".num_batches_tracked"] = sd[pre + ".num_batches_tracked"] + 1
+        return y
+
+    h = x
+    for ci, bi in PRETRAIN_ENC:
+        h = F.conv2d(h, sd[f"encoder.{ci}.weight"], sd[f"encoder.{ci}.bias"], stride=2, padding=1)
+        if bi is not None:
+            h = bn(h, f"encoder.{bi}")
+        h = F.leaky_relu(h, 0.2)
+    for ci, bi in PRETRAIN_DEC:
+        h = F.conv_transpose2d(h, sd[f"decoder.{ci}.weight"], sd[f"decoder.{ci}.bias"], stride=2, padding=1)
+        if bi is not None:
+            h = torch.relu(bn(h, f"decoder.{bi}"))
+    return torch.tanh(h), new
+
+
+def pretrain_masked_l1(generated, real, mask):
+    """pretrain.py:160: nn.L1Loss()(generated * (1 - masks), real * (1 - masks))."""
+    return (generated * (1 - mask) - real * (1 - mask)).abs().mean()
+
+
+# --------------------------------------------------------------------------------------------
 # Gram / VGG style loss (north_star addition; NOT in the reference, parity unpinned)
 # --------------------------------------------------------------------------------------------
 VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512]

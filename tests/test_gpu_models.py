@@ -356,3 +356,64 @@ def test_c64_bf16_odd_plane_geometries_track_fp32(hw):
     assert torch.isfinite(y16).all()
     _, l2b = parity_errors(y16_0, y16[:1])
     assert l2b <= 1e-2, l2b
+
+
+def _pretrain_model(g, precision):
+    from multi_style_transfer_gan_b200.pretrain import Generator
+    torch.manual_seed(0)
+    G = Generator(channels=8).to(DEV)
+    G.load_state_dict(g["init"], strict=True)
+    return G.set_precision(precision)
+
+
+def test_pretrain_generator_golden_fp32(golden):
+    """pretrain.Generator (pretrain.py:60-97, BatchNorm auto-encoder) on the msg_b200 kernels vs the golden from the
+    unmodified reference: train-mode forward (batch statistics), masked-L1 loss (:160), every gradient, the running
+    statistics update, and the eval-mode forward (running statistics)."""
+    from multi_style_transfer_gan_b200.losses import l1
+    g = golden("pretrain_c8_64.pt")
+    G = _pretrain_model(g, "fp32").train()
+    x = g["masked"].to(DEV).requires_grad_(True)
+    real, mask = g["real"].to(DEV), g["mask"].to(DEV)
+    y = G(x)
+    assert_parity(y, g["y_train"], 1e-4, "pretrain y (train)")
+    loss = l1(y * (1 - mask), real * (1 - mask))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5
+    loss.backward()
+    assert_parity(x.grad, g["dx"], 2e-2, "pretrain dx")
+    for k, p in G.named_parameters():
+        ref = g["grads"][k]
+        if float(ref.abs().max()) < 1e-7:      # conv biases in front of a BatchNorm: analytically zero, pure noise
+            assert float(p.grad.abs().max()) < 1e-5, k
+            continue
+        assert_parity(p.grad, ref, 2e-2, f"pretrain grad {k}")
+    sd = G.state_dict()
+    for k, ref in g["running_after"].items():
+        assert torch.allclose(sd[k].double().cpu(), ref.double(), rtol=1e-4, atol=1e-6), k
+    G.eval()
+    with torch.no_grad():
+        y_eval = G(g["masked"].to(DEV))
+    assert_parity(y_eval, g["y_eval"], 1e-4, "pretrain y (eval)")
+    with pytest.raises(RuntimeError):
+        G(torch.zeros(1, 3, 40, 64, device=DEV))
+
+
+def test_pretrain_generator_bf16_and_step(golden):
+    """bf16 (the reference trains under autocast, pretrain.py:158) tracks fp32, and the masked-L1 step with gradient
+    clipping (:159-166) reduces the loss on a fixed batch."""
+    from multi_style_transfer_gan_b200.enhanced_train import FusedAdam
+    from multi_style_transfer_gan_b200.pretrain import Generator, pretrain_step
+    g = golden("pretrain_c8_64.pt")
+    G = _pretrain_model(g, "bf16").train()
+    with torch.no_grad():
+        y = G(g["masked"].to(DEV))
+    _, l2 = parity_errors(y, g["y_train"])
+    assert l2 <= 5e-2, l2
+    torch.manual_seed(1)
+    G = Generator(channels=64).to(DEV).set_precision("bf16").train()
+    opt = FusedAdam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    real = synth_images(4, 128, 128, seed=3).to(DEV)
+    mask = (torch.rand(4, 1, 128, 128, device=DEV) > 0.3).float()
+    losses = [pretrain_step(G, opt, real * mask, real, mask) for _ in range(12)]
+    assert all(math.isfinite(v) for v in losses)
+    assert losses[-1] < losses[0], losses

@@ -61,3 +61,25 @@ def test_oracle_restatement_matches_live_reference():
         s2, st2, _ = R.discriminator_forward(dict(D.state_dict()), x, training=False)
     assert_parity(s2, s, 1e-4, "score")
     assert_parity(st2, st, 1e-4, "struct")
+
+
+@pytest.mark.parametrize("c", [64, 8])
+def test_pretrain_generator_init_bit_identical(c):
+    """pretrain.Generator (pretrain.py:60-97): same module tree, state_dict keys (incl. BatchNorm buffers) and default
+    init in the same RNG order."""
+    import importlib
+    from oracle import ref_import
+    ref_import.load()
+    pt = importlib.import_module("pretrain")
+    from multi_style_transfer_gan_b200.pretrain import Generator
+    torch.manual_seed(3)
+    ref = pt.Generator(channels=c)
+    torch.manual_seed(3)
+    mine = Generator(channels=c)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    mine.load_state_dict(rs, strict=True)
+    ref.load_state_dict(ms, strict=True)

@@ -124,3 +124,27 @@ def test_gram_properties():
     torch.testing.assert_close(G, G.transpose(1, 2))
     assert (torch.linalg.eigvalsh(G.double()) > -1e-9).all()
     assert float(R.style_loss([f], [f])) == 0.0
+
+
+def test_pretrain_generator(golden):
+    """oracle restatement of pretrain.Generator (BatchNorm auto-encoder) against the golden from the unmodified
+    reference: train-mode forward, running-statistics update, masked-L1 loss and its gradients, eval-mode forward."""
+    g = golden("pretrain_c8_64.pt")
+    sd = {k: v.clone() for k, v in g["init"].items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd.update(params)
+    x = g["masked"].clone().requires_grad_(True)
+    y, new = R.pretrain_generator_forward(sd, x, training=True)
+    assert_parity(y, g["y_train"], 1e-6, "pretrain y (train mode)")
+    loss = R.pretrain_masked_l1(y, g["real"], g["mask"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    loss.backward()
+    assert_parity(x.grad, g["dx"], 1e-4, "pretrain dx")
+    for k, ref in g["grads"].items():
+        assert_parity(params[k].grad, ref, 1e-4, f"pretrain grad {k}")
+    for k, ref in g["running_after"].items():
+        assert torch.allclose(new[k].double(), ref.double(), rtol=1e-6, atol=1e-7), k
+    sd2 = {k: v.detach() for k, v in sd.items()}
+    sd2.update(g["running_after"])
+    y_eval, _ = R.pretrain_generator_forward(sd2, g["masked"], training=False)
+    assert_parity(y_eval, g["y_eval"], 1e-6, "pretrain y (eval mode)")
