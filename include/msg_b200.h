@@ -45,6 +45,8 @@ extern "C" {
 #define MSG_CONV_STATS 1u      /* accumulate per-(n,cout) sum / sum-of-squares of the output   */
 #define MSG_CONV_OUT_NCHW_F32 2u /* write the result as fp32 NCHW (final image, Cout small)     */
 #define MSG_CONV_ACCUM 8u      /* y += result (sums the gradient branches of a fan-out)          */
+#define MSG_CONV_PER_IMAGE_W 16u /* w holds one packed weight per image, [N][Cout][KH*KW*Cin]: a batched
+                                   * "matrix times per-image matrix" (Gram backward).  bf16 TMA kernel only.    */
 #define MSG_CONV_FORCE_GATHER 512u /* debugging: skip the TMA kernel, use the cp.async gather kernel  */
 #define MSG_CONV_FORCE_SIMT 256u /* debugging: never take the tcgen05 path                      */
 #define MSG_CONV_IN_NORM 4u    /* normalise the INPUT on load with in_stats (IN + act fused

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmsg_b200.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 CONV_STATS, CONV_OUT_NCHW_F32, CONV_IN_NORM, CONV_ACCUM, CONV_FORCE_SIMT, CONV_FORCE_GATHER = 1, 2, 4, 8, 256, 512
+CONV_PER_IMAGE_W = 16
 PACK_FWD, PACK_DGRAD_S1, PACK_CONVT_PHASES = 0, 1, 2
 
 c_int, c_ll, c_float, c_void_p, c_uint = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float,

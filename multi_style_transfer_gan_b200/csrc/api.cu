@@ -61,9 +61,12 @@ int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const 
   if (!(d->flags & MSG_CONV_FORCE_SIMT)) {
     if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_tma_supported(d, x, w, y))
       return conv2d_tma(d, x, w, bias, y, stats, in_stats, st);            // persistent TMA + tcgen05 kernel
+    MSG_REQUIRE(!(d->flags & MSG_CONV_PER_IMAGE_W), MSG_ERR_UNSUPPORTED,
+                "conv: MSG_CONV_PER_IMAGE_W needs the TMA kernel (bf16, Cin % 64 == 0, plane a multiple of 128 pixels)");
     if (conv2d_tc_supported(d, x, w, y))
       return conv2d_tc(d, x, w, bias, y, stats, in_stats, st);   // cp.async gather + tcgen05 kernel
   }
+  MSG_REQUIRE(!(d->flags & MSG_CONV_PER_IMAGE_W), MSG_ERR_UNSUPPORTED, "conv: MSG_CONV_PER_IMAGE_W needs the TMA kernel");
   return conv2d_simt(d, x, w, bias, y, stats, in_stats, st);
 }
 

@@ -224,6 +224,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int rg = rem / tiles_per_row, cg = rem - rg * tiles_per_row;
         const int i0 = rg * p.R, j0 = cg * p.Wt;
         const int w_base = j0 * d.in_stride - d.pad_w, h_base = i0 * d.in_stride - d.pad_h;
+        const int w_row0 = (d.flags & MSG_CONV_PER_IMAGE_W) ? img * d.Cout : 0;   // per-image weights: row block of this image
         int kb = 0;
         for (int th = 0; th < d.KH; ++th)
           for (int tw = 0; tw < d.KW; ++tw)
@@ -231,7 +232,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
               mbar_expect_tx(full_bar(s), A_BYTES + (p.b_resident ? 0 : b_bytes));
               tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), cb * BK, w_base + tw * d.dil, h_base + th * d.dil, img);
-              if (!p.b_resident) tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN);
+              if (!p.b_resident) tma_load_2d(sB + s * b_bytes, &mapB, full_bar(s), kb * BK, nt * BN + w_row0);
               if (++s == S) { s = 0; ph ^= 1u; wrapped = true; }   // no per-K-block div/mod by the runtime stage count
             }
       }
@@ -593,6 +594,7 @@ bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, 
   if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
   if (!(d->flags & MSG_CONV_OUT_NCHW_F32) && ((uintptr_t)y & 15)) return false;
   if (d->in_stride != 1 && d->in_stride != 2) return false;
+  if ((d->flags & MSG_CONV_PER_IMAGE_W) && ((long long)d->Hg * d->Wg) % BM) return false;   // tiles inside one image
   Tiling t;
   if (!pick_tiling(d, &t)) return false;
   if (t.Wt * d->in_stride > 256 || t.R * d->in_stride > 256) return false;
@@ -619,7 +621,7 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
   while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int K = d->KH * d->KW * d->Cin;
   static const bool env_bres = [] { const char* e = getenv("MSG_TMA_BRESIDENT"); return !(e && e[0] == '0'); }();
-  p.b_resident = (env_bres && p.n_tiles == 1 && p.nkb * p.BN * BK * 2 <= 64 * 1024) ? 1 : 0;
+  p.b_resident = (env_bres && p.n_tiles == 1 && p.nkb * p.BN * BK * 2 <= 64 * 1024 && !(d->flags & MSG_CONV_PER_IMAGE_W)) ? 1 : 0;
   const int bres_bytes = p.b_resident ? p.nkb * p.BN * BK * 2 : 0;
   const int stage_bytes = A_BYTES + (p.b_resident ? 0 : p.BN * BK * 2);
   // two epilogue groups when the extra staging / scratch (57 KB) still leaves >= 3 pipeline stages
@@ -656,7 +658,7 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d->Cout};
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d->Cout * ((d->flags & MSG_CONV_PER_IMAGE_W) ? d->N : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p.BN};
     cuuint32_t es[2] = {1, 1};

@@ -97,6 +97,9 @@ struct WgParams {
   int co_tiles;          // ceil(Cout / 128)
   int splits;            // pixel-range splits
   int stages;
+  int per_image;         // 1: every image accumulates into its own [Cout][K] block (batched Gram matrices); the
+                         //    pixel-range splits then never straddle an image (splits = N * splits_per_image)
+  int splits_per_image;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -113,8 +116,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
   const int cot = w / p.groups;
   const int pair0 = grp * MAXP;
   const int npair = (p.n_pairs - pair0) < MAXP ? (p.n_pairs - pair0) : MAXP;
-  const int mt_begin = (int)((long long)split * p.m_tiles / p.splits);
-  const int mt_end = (int)((long long)(split + 1) * p.m_tiles / p.splits);
+  int mt_begin, mt_end, out_img = 0;
+  if (p.per_image) {
+    const int tpi = p.m_tiles / d.N;                       // M tiles per image
+    out_img = split / p.splits_per_image;
+    const int sub = split - out_img * p.splits_per_image;
+    mt_begin = out_img * tpi + (int)((long long)sub * tpi / p.splits_per_image);
+    mt_end = out_img * tpi + (int)((long long)(sub + 1) * tpi / p.splits_per_image);
+  } else {
+    mt_begin = (int)((long long)split * p.m_tiles / p.splits);
+    mt_end = (int)((long long)(split + 1) * p.m_tiles / p.splits);
+  }
   const int stage_bytes = (2 + MAXP) * TILE;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -209,7 +221,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       for (int pi = 0; pi < npair; ++pi) {
         const int pr = pair0 + pi;
         const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
-        float* dst = p.dw + (size_t)co * Ktot + (size_t)tap * d.Cin + cb * 64;
+        float* dst = p.dw + (size_t)out_img * d.Cout * Ktot + (size_t)co * Ktot + (size_t)tap * d.Cin + cb * 64;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           __syncwarp();
@@ -272,7 +284,17 @@ bool conv2d_wgrad_tc_supported(const msg_conv_desc* d, const void* x, const void
   return get_encode() != nullptr;
 }
 
+int conv2d_wgrad_tc_impl(const msg_conv_desc* d, const void* x, const void* dy, float* dw, bool per_image, cudaStream_t st);
 int conv2d_wgrad_tc(const msg_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  return conv2d_wgrad_tc_impl(d, x, dy, dw, false, st);
+}
+// dw[n] += dY[n]^T X[n] for every image n separately: dw is [N][Cout][KH*KW*Cin] fp32 (zeroed by the caller).
+// With x == dy and a 1x1 geometry this is the batch of Gram matrices F^T F (gram.cu).
+int conv2d_wgrad_tc_per_image(const msg_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  return conv2d_wgrad_tc_impl(d, x, dy, dw, true, st);
+}
+
+int conv2d_wgrad_tc_impl(const msg_conv_desc* d, const void* x, const void* dy, float* dw, bool per_image, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled unavailable");
   WgParams p;
@@ -287,6 +309,17 @@ int conv2d_wgrad_tc(const msg_conv_desc* d, const void* x, const void* dy, float
   int splits = (2 * sm_count() + items - 1) / items;     // ~2 CTAs' worth of work items per SM in total
   if (splits > p.m_tiles) splits = p.m_tiles;
   if (splits < 1) splits = 1;
+  p.per_image = per_image ? 1 : 0;
+  p.splits_per_image = 1;
+  if (per_image) {
+    MSG_REQUIRE(p.m_tiles % d->N == 0, MSG_ERR_SHAPE, "wgrad_tc: per-image mode needs whole tiles per image");
+    const int tpi = p.m_tiles / d->N;
+    int spi = (2 * sm_count() + items * d->N - 1) / (items * d->N);
+    if (spi > tpi) spi = tpi;
+    if (spi < 1) spi = 1;
+    p.splits_per_image = spi;
+    splits = spi * d->N;
+  }
   p.splits = splits;
   p.stages = 2;
   const size_t smem = (size_t)p.stages * (2 + MAXP) * TILE + 8 * (2 * p.stages + 1) + 16 + 1024;

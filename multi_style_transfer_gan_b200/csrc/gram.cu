@@ -3,15 +3,36 @@
 // oracle/restate.py::gram / style_loss (Gatys / Johnson formulation), parity unpinned vs reference.
 //
 // Features are [N][HW][C] (channel-contiguous), so F F^T is a "pixels are K" GEMM with both
-// operands MN-major.  SIMT engine: 64x64 (a,b) tiles, split over pixels, fp32 atomics.
-// Backward:  dF = coef * (G - A) . F  is a 1x1 convolution with per-image weight (G - A), and is
-// issued through the generic conv path (conv_tc.cu for bf16).
+// operands MN-major -- exactly the weight-gradient GEMM of a 1x1 conv with x = dy = F.  bf16 features with
+// C % 64 == 0 and HW % 128 == 0 therefore run on the tcgen05 wgrad kernel (conv_wgrad_tc.cu) in its per-image
+// mode: ONE launch produces the whole batch of Gram matrices straight from TMA boxes of F.  Everything else
+// (fp32 parity mode, odd shapes) takes the SIMT engine below: 64x64 (a,b) tiles, split over pixels, fp32 atomics.
+// Backward:  dF = coef * (G - A) . F  is a 1x1 convolution with a per-image weight (G - A): one launch of the
+// TMA conv kernel with MSG_CONV_PER_IMAGE_W (a per-image loop over the generic conv path otherwise).
 #include "common.cuh"
 
 namespace msg {
 int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     double* stats, const double* in_stats, cudaStream_t st);
+bool conv2d_tma_supported(const msg_conv_desc* d, const void* x, const void* w, const void* y);
+bool conv2d_wgrad_tc_supported(const msg_conv_desc* d, const void* x, const void* dy);
+int conv2d_wgrad_tc_per_image(const msg_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
 namespace {
+
+// [N][HW][C] features as the input AND output of a 1x1 "convolution" over a 1 x HW plane
+msg_conv_desc plane_desc(int dtype, int N, long long HW, int C) {
+  msg_conv_desc d = {};
+  d.dtype = dtype; d.N = N; d.Hi = 1; d.Wi = (int)HW; d.Ci_total = C; d.ci_off = 0; d.Cin = C;
+  d.Ho = 1; d.Wo = (int)HW; d.Co_total = C; d.co_off = 0; d.Cout = C; d.Hg = 1; d.Wg = (int)HW;
+  d.KH = 1; d.KW = 1; d.in_stride = 1; d.pad_h = 0; d.pad_w = 0; d.dil = 1;
+  d.out_stride = 1; d.out_off_h = 0; d.out_off_w = 0; d.act = MSG_ACT_NONE; d.flags = 0;
+  return d;
+}
+
+__global__ void scale_kernel(float* __restrict__ g, long long n, float s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] *= s;
+}
 
 constexpr int GP = 16;
 template <typename T>
@@ -108,6 +129,16 @@ __global__ void gram_diff_weight_kernel(const float* __restrict__ g, const float
 template <typename T>
 int gram_impl(const T* f, int N, long long HW, int C, float* gram, cudaStream_t st) {
   cudaMemsetAsync(gram, 0, (size_t)N * C * C * sizeof(float), st);
+  if (sizeof(T) == 2 && HW <= 0x7fffffffLL && HW % 128 == 0 && C % 64 == 0) {
+    const msg_conv_desc d = plane_desc(MSG_BF16, N, HW, C);
+    if (conv2d_wgrad_tc_supported(&d, f, f)) {            // tcgen05: G[n] = F[n]^T F[n] for the whole batch, one launch
+      int rc = conv2d_wgrad_tc_per_image(&d, f, f, gram, st);
+      if (rc) return rc;
+      const long long n = (long long)N * C * C;
+      scale_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(gram, n, 1.f / ((float)C * (float)HW));
+      return check_launch("gram scale_kernel");
+    }
+  }
   int tiles = (C + 63) / 64;
   long long pairs = (long long)tiles * tiles;
   long long want = (4LL * sm_count()) / (pairs * N) + 1;
@@ -163,12 +194,13 @@ extern "C" int msg_gram_loss_bwd(int dtype, const void* feat, int N, long long H
   else if (dtype == MSG_BF16) gram_diff_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(gram, target, n, coef, (__nv_bfloat16*)wbuf);
   else MSG_REQUIRE(false, MSG_ERR_UNSUPPORTED, "gram_bwd: bad dtype");
   int rc = check_launch("gram_diff_weight_kernel");
-  // one 1x1 "convolution" per image: [HW x C] = F[HW x C] . W^T, W = coef*(G-A) [Cout=C][Cin=C]
-  msg_conv_desc d = {};
-  d.dtype = dtype; d.N = 1; d.Hi = 1; d.Wi = (int)HW; d.Ci_total = C; d.ci_off = 0; d.Cin = C;
-  d.Ho = 1; d.Wo = (int)HW; d.Co_total = C; d.co_off = 0; d.Cout = C; d.Hg = 1; d.Wg = (int)HW;
-  d.KH = 1; d.KW = 1; d.in_stride = 1; d.pad_h = 0; d.pad_w = 0; d.dil = 1;
-  d.out_stride = 1; d.out_off_h = 0; d.out_off_w = 0; d.act = MSG_ACT_NONE; d.flags = 0;
+  if (rc) return rc;
+  // [HW x C] = F[HW x C] . W^T per image, W = coef*(G-A) [Cout=C][Cin=C]
+  msg_conv_desc db = plane_desc(dtype, N, HW, C);
+  db.flags = MSG_CONV_PER_IMAGE_W;
+  if (dtype == MSG_BF16 && conv2d_tma_supported(&db, feat, wbuf, dfeat))
+    return conv2d_dispatch(&db, feat, wbuf, nullptr, dfeat, nullptr, nullptr, st);     // whole batch, one launch
+  msg_conv_desc d = plane_desc(dtype, 1, HW, C);
   for (int i = 0; i < N && rc == MSG_OK; ++i) {
     const char* fi = (const char*)feat + (size_t)i * HW * C * esz;
     char* di = (char*)dfeat + (size_t)i * HW * C * esz;
