@@ -98,14 +98,18 @@ gram_kernel(const T* __restrict__ f, long long HW, int C, float inv_norm, float*
   }
 }
 
+// loss += scale * mean((g*gs - a)^2); with gs != 1 the normalised Gram matrices are also written back (the
+// tensor-core GEMM leaves raw sums: its normalisation is fused into this pass)
 __global__ void __launch_bounds__(256)
-gram_mse_kernel(const float* __restrict__ g, const float* __restrict__ a, long long n, float scale,
+gram_mse_kernel(float* __restrict__ g, const float* __restrict__ a, long long n, float gs, float scale,
                 float* __restrict__ loss) {
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    float d = g[i] - a[i];
+    float gv = g[i];
+    if (gs != 1.f) { gv *= gs; g[i] = gv; }
+    float d = gv - a[i];
     acc = fmaf(d, d, acc);
   }
   acc = warp_sum(acc);
@@ -126,16 +130,21 @@ __global__ void gram_diff_weight_kernel(const float* __restrict__ g, const float
     w[i] = from_f<T>(coef * (g[i] - a[i]));
 }
 
+// pending_scale: when non-null and the tensor-core path ran, the 1/(C*HW) normalisation is NOT applied and
+// *pending_scale receives it (the caller fuses it into its next pass over the matrices); else it is set to 1.
 template <typename T>
-int gram_impl(const T* f, int N, long long HW, int C, float* gram, cudaStream_t st) {
+int gram_impl(const T* f, int N, long long HW, int C, float* gram, cudaStream_t st, float* pending_scale = nullptr) {
+  if (pending_scale) *pending_scale = 1.f;
   cudaMemsetAsync(gram, 0, (size_t)N * C * C * sizeof(float), st);
   if (sizeof(T) == 2 && HW <= 0x7fffffffLL && HW % 128 == 0 && C % 64 == 0) {
     const msg_conv_desc d = plane_desc(MSG_BF16, N, HW, C);
     if (conv2d_wgrad_tc_supported(&d, f, f)) {            // tcgen05: G[n] = F[n]^T F[n] for the whole batch, one launch
       int rc = conv2d_wgrad_tc_per_image(&d, f, f, gram, st);
       if (rc) return rc;
+      const float inv_norm = 1.f / ((float)C * (float)HW);
+      if (pending_scale) { *pending_scale = inv_norm; return MSG_OK; }
       const long long n = (long long)N * C * C;
-      scale_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(gram, n, 1.f / ((float)C * (float)HW));
+      scale_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(gram, n, inv_norm);
       return check_launch("gram scale_kernel");
     }
   }
@@ -168,11 +177,16 @@ extern "C" int msg_gram(int dtype, const void* feat, int N, long long HW, int C,
 extern "C" int msg_gram_loss_fwd(int dtype, const void* feat, int N, long long HW, int C,
                                  const float* target, float scale, float* gram, float* loss_out,
                                  void* stream) {
-  int rc = msg_gram(dtype, feat, N, HW, C, gram, stream);
+  MSG_REQUIRE(N > 0 && HW > 0 && C > 0, MSG_ERR_SHAPE, "gram: bad shape");
+  float gs = 1.f;
+  int rc;
+  if (dtype == MSG_F32) rc = gram_impl<float>((const float*)feat, N, HW, C, gram, as_stream(stream), &gs);
+  else if (dtype == MSG_BF16) rc = gram_impl<__nv_bfloat16>((const __nv_bfloat16*)feat, N, HW, C, gram, as_stream(stream), &gs);
+  else MSG_REQUIRE(false, MSG_ERR_UNSUPPORTED, "gram: bad dtype");
   if (rc) return rc;
   long long n = (long long)N * C * C;
   unsigned blocks = (unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
-  gram_mse_kernel<<<blocks, 256, 0, as_stream(stream)>>>(gram, target, n, scale, loss_out);
+  gram_mse_kernel<<<blocks, 256, 0, as_stream(stream)>>>(gram, target, n, gs, scale, loss_out);
   return check_launch("gram_mse_kernel");
 }
 
