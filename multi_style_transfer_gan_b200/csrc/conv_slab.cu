@@ -27,8 +27,10 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS_MAX = 352;       // producer + MMA issuer A + up to two epilogue groups of four warps + MMA issuer B
 constexpr int STAGE_PITCH = 128 + 16;
+constexpr int EPI_STAGE = 4 * 32 * STAGE_PITCH;          // per epilogue group: four per-warp skewed staging tiles
+constexpr int EPI_RED = 16384 + 4 * 1056 * 4;            // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][33]
 
 
 struct SlabParams {
@@ -46,33 +48,68 @@ struct SlabParams {
   int segs;           // 128-pixel segments per image row
   int a_rows;         // pixel-pair mode: input rows per slab (consecutive filter rows fused into ONE K block)
   int b_tiles;        // weight tiles in w_slab (= taps, or filter rows in pixel-pair mode)
+  int interleave;     // tile schedule: 0 = contiguous range per CTA, 1 = round-robin over the grid
+  int epi_groups;     // 1: warps 2-5 drain both accumulator buffers; 2: warps 2-5 own buffer 0, warps 6-9 buffer 1
+  int issuers;        // 1: warp 1 issues every MMA; 2: the taps are split between warp 1 and the last warp by ACCUMULATOR COLUMN
+                      //    SLICE (tap_owner), so the two instruction streams never touch the same TMEM columns and need no
+                      //    ordering between them -- the issue loop is ONE thread's serial instruction stream and, for the
+                      //    small-N programs, slower than the tensor pipe (ncu: issuer 85 % busy, pipe 12-18 %)
+  unsigned char tap_owner[MSG_SLAB_MAX_TAPS];   // issuer of each tap
   int a_mode;         // 0: chunk planes [chunk][pixel][16 B], no swizzle (8 TMA boxes per slab)
                       // 1: pixel rows [pixel][128 B], 128B swizzle, ONE TMA box; tap shift = +128 B/pixel on the
                       //    descriptor start, swizzle phase carried by the descriptor's base_offset field
                       // 2: as 1 with base_offset = 0
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// ---- compile-time description of the fused MultiScaleBlock forward program (slab.py: msb_program) ----------------
+// K blocks: dy in (-4,-2,-1,0,1,2,4) x channel block; taps of a K block in branch order b1 (dy == 0 only), then the three
+// horizontal taps of every 3x3 branch whose dilation d has |dy| in {0, d}.  Knowing this at compile time turns the
+// issue loop into straight-line code with immediate operands (~5 instructions per MMA instead of ~14): the generic
+// loop is ONE thread's serial instruction stream and was slower than the tensor pipe (ncu: issuer 85 % busy).
+struct MsbTap { int sx, branch; };
+__host__ __device__ constexpr int msb_dy(int dyi) { return dyi == 0 ? -4 : dyi == 1 ? -2 : dyi == 2 ? -1 : dyi == 3 ? 0 : dyi == 4 ? 1 : dyi == 5 ? 2 : 4; }
+__host__ __device__ constexpr int msb_ntaps(int dyi) { return dyi == 3 ? 10 : 3; }
+__host__ __device__ constexpr MsbTap msb_tap(int dyi, int j) {
+  if (dyi == 3) {                       // centre row: b1, then b2 / b3 / b4 with sx = -d, 0, d
+    if (j == 0) return MsbTap{0, 0};
+    const int b = 1 + (j - 1) / 3, d = b == 1 ? 1 : b == 2 ? 2 : 4;
+    return MsbTap{((j - 1) % 3 - 1) * d, b};
+  }
+  const int dy = msb_dy(dyi), ad = dy < 0 ? -dy : dy;
+  const int b = ad == 1 ? 1 : ad == 2 ? 2 : 3;
+  return MsbTap{(j - 1) * ad, b};
+}
+__host__ __device__ constexpr int msb_first_dyi(int branch) { return branch == 0 ? 3 : branch == 1 ? 2 : branch == 2 ? 1 : 0; }
+__host__ __device__ constexpr int msb_taps_before(int dyi) {   // taps of one channel block in the K blocks before row dyi
+  int n = 0;
+  for (int i = 0; i < dyi; ++i) n += msb_ntaps(i);
+  return n;
+}
+
+template <int MSBC>      // 0: generic program from the descriptor; 64 / 128: the MultiScaleBlock forward program of that width
+__global__ void __launch_bounds__(NTHREADS_MAX, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   const msg_slab_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
+  const int G = p.epi_groups;
+  const int mma_b_warp = 2 + 4 * G;                          // second MMA issuer (issuers == 2)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sB = base;                                   // weight tiles first: 1024-byte aligned
   const uint32_t sA = sB + (p.b_resident ? p.b_resident : S * p.b_bytes);
   const uint32_t sStage = (sA + S * p.a_bytes + 127u) & ~127u;
-  const uint32_t sRed = sStage + 4 * 32 * STAGE_PITCH;        // per-warp column sums [4][2][256] floats
-  const uint32_t sBias = sRed + 16384 + 4 * 1056 * 4;                        // bias staged once per CTA (Ntot <= 256 floats)
+  const uint32_t sRed = sStage + G * EPI_STAGE;               // per group: per-warp column sums [4][2][256] + transpose scratch
+  const uint32_t sBias = sRed + G * EPI_RED;                  // bias staged once per CTA (Ntot <= 256 floats)
   const uint32_t sBar = sBias + 1024;
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
   float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
   const bool bias_in_smem = p.bias != nullptr;
   if (bias_in_smem)
-    for (int i = tid; i < d.Ntot; i += NTHREADS) sbias[i] = p.bias[i];
+    for (int i = tid; i < d.Ntot; i += (int)blockDim.x) sbias[i] = p.bias[i];
   const uint32_t wres_bar = sBar + 8u * (2 * S + 4);          // "resident weights have landed"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
@@ -82,8 +119,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)p.issuers); }
+      for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), (uint32_t)p.issuers); mbar_init(tempty_bar(b), 4); }
       mbar_init(wres_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -93,14 +130,25 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+  } else if (warp == 2 && p.a_mode != 0) {
+    // swizzled-slab mode: tile-invariant tap operands {A offset, B offset, TMEM column, overwrite} in 16-byte
+    // descriptor units, one 16-byte smem entry per tap, so the elected lane's issue loop is one LDS.128 + three
+    // adds per tap instead of a chain of indexed constant loads
+    uint4* tt = reinterpret_cast<uint4*>(gen + (sBar + 256u - base));
+    for (int tp = lane; tp < d.n_taps; tp += 32)
+      tt[tp] = make_uint4((uint32_t)d.tap_sx[tp] >> 4, (uint32_t)d.tap_kstep[tp] >> 4, (uint32_t)d.tap_acc_col[tp],
+                          (uint32_t)d.tap_first[tp] | ((uint32_t)p.tap_owner[tp] << 1));
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = d.N * d.H * p.segs;
-  const int t_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);   // contiguous range per CTA
-  const int t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  // tile schedule: CTA-contiguous ranges (tstep = 1), or round-robin (tstep = grid): then all CTAs work on neighbouring
+  // rows of the same image at any time, so every input row comes from DRAM once and its 7 re-reads (one per dy) hit L2
+  const int tstep = p.interleave ? (int)gridDim.x : 1;
+  const int t_begin = p.interleave ? (int)blockIdx.x : (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int t_end = p.interleave ? total_tiles : (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
   const int tap_bytes = d.ncols * 128;
 
   if (warp == 0) {
@@ -115,7 +163,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       bool wrapped = false;
-      for (int t = t_begin; t < t_end; ++t) {
+      for (int t = t_begin; t < t_end; t += tstep) {
         const int seg = t % p.segs, ny = t / p.segs;
         const int yrow = ny % d.H, img = ny / d.H;
         const int x0 = seg * BM - d.halo;
@@ -142,8 +190,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || (p.issuers == 2 && warp == mma_b_warp)) {
+    // ===================================== MMA issuer(s) =====================================
+    const int issuer = warp == 1 ? 0 : 1;
     // The WHOLE warp runs this loop (warp-uniform control flow, per-tap constants read from the kernel
     // parameters = constant bank) so that descriptors stay in uniform registers; only the tcgen05
     // instructions themselves are issued by one elected lane.
@@ -167,17 +216,53 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // swizzled-slab mode: tile-invariant tap operands {A offset, B offset, TMEM column, overwrite} in 16-byte
     // descriptor units, one 16-byte smem entry per tap, so the elected lane's issue loop is one LDS.128 + three
     // adds per tap instead of a chain of indexed constant loads
-    uint4* tap_tab = reinterpret_cast<uint4*>(gen + (sBar + 256u - base));
-    if (p.a_mode != 0) {
-      for (int tp = lane; tp < d.n_taps; tp += 32)
-        tap_tab[tp] = make_uint4((uint32_t)d.tap_sx[tp] >> 4, (uint32_t)d.tap_kstep[tp] >> 4, (uint32_t)d.tap_acc_col[tp],
-                                 (uint32_t)d.tap_first[tp]);
-      __syncwarp();
-    }
+    const uint4* tap_tab = reinterpret_cast<const uint4*>(gen + (sBar + 256u - base));   // built before the block barrier
     int s = 0;
     uint32_t ph = 0, lt = 0;
     if (p.b_resident) mbar_wait(wres_bar, 0);
-    for (int t = t_begin; t < t_end; ++t, ++lt) {
+    if constexpr (MSBC != 0) {
+      // ---- specialised straight-line issue: every tap operand is an immediate --------------------------------
+      constexpr int CB = MSBC / 64, Q = MSBC / 4, TAPU = Q * 8;      // weight tile of one tap in 16-byte units
+      const uint32_t hi = (uint32_t)(sw128_hi >> 32);
+      const bool leader = elect_one();
+      const uint32_t a_base = sA >> 4, a_step = (uint32_t)p.a_bytes >> 4;
+      const uint32_t b_base = sB >> 4, b_step = (uint32_t)p.b_bytes >> 4;
+      const bool bres = p.b_resident != 0;
+      for (int t = t_begin; t < t_end; t += tstep, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * MSBC);
+#pragma unroll
+        for (int dyi = 0; dyi < 7; ++dyi) {
+#pragma unroll
+          for (int cb = 0; cb < CB; ++cb) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const int tp0 = msb_taps_before(dyi) * CB + cb * msb_ntaps(dyi);     // program-order index of this K block's first tap
+            const uint32_t a0 = a_base + (uint32_t)s * a_step;
+            const uint32_t b0 = bres ? b_base + (uint32_t)(tp0 * TAPU) : b_base + (uint32_t)s * b_step;
+            if (leader) {
+#pragma unroll
+              for (int j = 0; j < msb_ntaps(dyi); ++j) {
+                const MsbTap tap = msb_tap(dyi, j);
+                const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16_lo(tacc + (uint32_t)(tap.branch * Q), a0 + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
+                               b0 + (uint32_t)(j * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+              }
+              umma_commit(empty_bar(s));
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
+        }
+        if (leader) umma_commit(tfull_bar(buf));
+        __syncwarp();
+      }
+    } else
+    for (int t = t_begin; t < t_end; t += tstep, ++lt) {
       const int buf = lt & 1;
       if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
       tc_fence_after();
@@ -196,6 +281,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             uint4 e = tap_tab[t0];
             for (int tp = t0; tp < t1; ++tp) {
               const uint4 nx = tap_tab[tp + 1 < t1 ? tp + 1 : tp];      // prefetch the next entry
+              if ((int)(e.w >> 1) != issuer) { e = nx; continue; }     // the other issuer's accumulator slice
+              e.w &= 1u;
               const uint64_t da = sw128_hi | (uint64_t)(a0s + e.x);
               const uint64_t db = sw128_hi | (uint64_t)(b0s + e.y);
               const uint32_t dcol = tacc + e.z;
@@ -248,17 +335,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       __syncwarp();
       if (elect_one()) umma_commit(tfull_bar(buf));
     }
-  } else {
-    // ===================================== epilogue (warps 2-5) =====================================
+  } else if (warp >= 2 && warp < 2 + 4 * G) {
+    // ===================================== epilogue (warps 2-5, and 6-9 with two groups) ===========
+    // With two groups, group g drains accumulator buffer g, i.e. every other tile: two epilogues in flight per scheduler.
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
-    uint8_t* stage_w = stage_gen + q * (32 * STAGE_PITCH);
+    uint8_t* stage_w = stage_gen + grp * EPI_STAGE + q * (32 * STAGE_PITCH);
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
-    double* wsum = reinterpret_cast<double*>(red) + q * 512;   // [2][256] running column sums of this warp (fp64 above the
+    double* wsum = reinterpret_cast<double*>(red + grp * (EPI_RED / 4)) + q * 512;   // [2][256] running column sums of this warp (fp64 above the
                                                                // fixed-order 32-row fp32 partials: grouping-independent)
-    float* tr = red + 4096 + q * 1056;            // [32][33] transpose scratch of this warp
+    float* tr = red + grp * (EPI_RED / 4) + 4096 + q * 1056;   // [32][33] transpose scratch of this warp
     for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1;
@@ -275,15 +364,16 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     };
     const bool vec = !nchw && ((d.Co_total | d.co_off | cmax) & 7) == 0;
     uint32_t lt = 0;
-    for (int t = t_begin; t < t_end; ++t, ++lt) {
+    for (int t = t_begin + (G == 2 ? grp * tstep : 0); t < t_end; t += G * tstep, ++lt) {
       const int seg = t % p.segs, ny = t / p.segs;
       const int yrow = ny % d.H, img = ny / d.H;
-      const int buf = lt & 1;
+      const int buf = G == 2 ? grp : (int)(lt & 1);                      // accumulator buffer of this tile
+      const uint32_t tf_parity = G == 2 ? (lt & 1) : ((lt >> 1) & 1);    // its (lt or lt/2)-th use
       const int xcol = seg * BM + row;
       const bool valid = xcol < d.W;
       const int opix = (img * d.H + yrow) * d.W + (valid ? xcol : 0);
       if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
-      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      mbar_wait(tfull_bar(buf), tf_parity);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains) + ((uint32_t)(q * 32) << 16);
       for (int cg = 0; cg < cmax; cg += 64) {
@@ -403,6 +493,27 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 
+// does the descriptor hold exactly the compile-time MultiScaleBlock program of width C?
+template <int C>
+bool is_msb_program(const msg_slab_desc* d) {
+  constexpr int CB = C / 64, Q = C / 4;
+  if (d->Cin != C || d->Ntot != C || d->ncols != Q || d->halo != 4 || d->pixel_pair_k || d->n_chains != 1 ||
+      d->n_kblocks != 7 * CB || d->n_taps != 28 * CB)
+    return false;
+  int tp = 0;
+  for (int dyi = 0; dyi < 7; ++dyi)
+    for (int cb = 0; cb < CB; ++cb) {
+      const int kb = dyi * CB + cb;
+      if (d->kb_dy[kb] != msb_dy(dyi) || d->kb_cb[kb] != cb || d->kb_tap_begin[kb] != tp) return false;
+      for (int j = 0; j < msb_ntaps(dyi); ++j, ++tp) {
+        const MsbTap t = msb_tap(dyi, j);
+        if (d->tap_sx[tp] != t.sx || d->tap_acc_col[tp] != t.branch * Q) return false;
+        if (d->tap_first[tp] != (cb == 0 && j == 0 && dyi == msb_first_dyi(t.branch) ? 1 : 0)) return false;
+      }
+    }
+  return d->kb_tap_begin[7 * CB] == tp;
+}
+
 }  // namespace
 }  // namespace msg
 
@@ -489,7 +600,54 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int fixed = 128 + 4 * 32 * STAGE_PITCH + 16384 + 4 * 1056 * 4 + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
+  static const int env_groups = [] { const char* e = getenv("MSG_SLAB_EPI_GROUPS"); return e ? atoi(e) : 0; }();
+  static const int env_issuers = [] { const char* e = getenv("MSG_SLAB_ISSUERS"); return e ? atoi(e) : 0; }();
+  auto fixed_for = [&](int groups) {
+    return 128 + groups * (EPI_STAGE + EPI_RED) + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
+  };
+  // A second epilogue group (every other tile) is available (MSG_SLAB_EPI_GROUPS=2) but off by default: measured on
+  // B200 the programs here are bound by shared-memory bandwidth (A re-read by every small-N MMA), not by the
+  // epilogue's instruction stream, and the group's staging costs pipeline stages (MSB C=64: 0.78 -> 0.90 ms).
+  p.epi_groups = 1;
+  if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
+  // straight-line issue code for the MultiScaleBlock forward programs (C = 64, 128)
+  static const bool env_spec = [] { const char* e = getenv("MSG_SLAB_SPECIALISE"); return !(e && e[0] == '0'); }();
+  const int spec = (!env_spec || p.a_mode == 0) ? 0 : is_msb_program<64>(d) ? 64 : is_msb_program<128>(d) ? 128 : 0;
+  // Two issuers split the taps by accumulator column slice (disjoint TMEM columns => no ordering between the two
+  // instruction streams): slices sorted by tap count, each given to the less loaded issuer.  Programs with a single
+  // slice (dgrad, 7x7 convs) and the pixel-pair / chunk-plane modes keep one issuer.
+  p.issuers = 1;
+  for (int tp = 0; tp < MSG_SLAB_MAX_TAPS; ++tp) p.tap_owner[tp] = 0;
+  if (spec == 0 && p.a_mode != 0 && d->n_chains == 1 && env_issuers != 1) {
+    int cols[MSG_SLAB_MAX_TAPS], cnt[MSG_SLAB_MAX_TAPS], ns = 0;
+    for (int tp = 0; tp < d->n_taps; ++tp) {
+      int i = 0;
+      while (i < ns && cols[i] != d->tap_acc_col[tp]) ++i;
+      if (i == ns) { cols[ns] = d->tap_acc_col[tp]; cnt[ns] = 0; ++ns; }
+      ++cnt[i];
+    }
+    if (ns >= 2) {
+      int load[2] = {0, 0}, owner[MSG_SLAB_MAX_TAPS];
+      bool used[MSG_SLAB_MAX_TAPS] = {false};
+      for (int k = 0; k < ns; ++k) {                  // largest slice first
+        int best = -1;
+        for (int i = 0; i < ns; ++i)
+          if (!used[i] && (best < 0 || cnt[i] > cnt[best])) best = i;
+        used[best] = true;
+        const int o = load[1] < load[0] ? 1 : 0;
+        owner[best] = o; load[o] += cnt[best];
+      }
+      for (int tp = 0; tp < d->n_taps; ++tp) {
+        int i = 0;
+        while (cols[i] != d->tap_acc_col[tp]) ++i;
+        p.tap_owner[tp] = (unsigned char)owner[i];
+      }
+      p.issuers = 2;
+    }
+  }
+  static const int env_il = [] { const char* e = getenv("MSG_SLAB_INTERLEAVE"); return e ? atoi(e) : -1; }();
+  p.interleave = env_il >= 0 ? env_il : 1;
+  const int fixed = fixed_for(p.epi_groups);
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_slab: stage of %d bytes does not fit twice in shared memory", stage_bytes);
@@ -522,7 +680,9 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -530,6 +690,9 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   const long long total = (long long)d->N * d->H * p.segs;
   MSG_REQUIRE(total < 0x7fffffffLL, MSG_ERR_SHAPE, "conv_slab: too many tiles");
   if (grid > total) grid = (int)total;
-  conv_slab_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(mapA, mapB, p);
+  const int nthreads = 64 + 128 * p.epi_groups + (p.issuers == 2 ? 32 : 0);
+  if (spec == 64) conv_slab_kernel<64><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (spec == 128) conv_slab_kernel<128><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else conv_slab_kernel<0><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
   return check_launch("conv_slab_kernel");
 }

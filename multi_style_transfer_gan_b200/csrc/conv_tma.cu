@@ -155,12 +155,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // index, and one elected lane issues the four MMAs and the commit of a K block.
     {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint64_t desc_hi = make_sw128_desc(0);
+      const uint32_t hi = (uint32_t)(make_sw128_desc(0) >> 32);     // constant high descriptor word (SBO, version, swizzle)
       const uint32_t a_base = sA >> 4, b_base = sB >> 4;
       const uint32_t a_step = A_BYTES >> 4, b_step = (uint32_t)b_bytes >> 4;
+      const bool leader = elect_one();        // one election for the whole kernel: no ELECT / reconvergence per K block
+      const bool bres = p.b_resident != 0;
       int s = 0;
       uint32_t ph = 0, lt = 0;
-      if (p.b_resident) mbar_wait(wres_bar, 0);
+      if (bres) mbar_wait(wres_bar, 0);
       for (int t = t_begin; t < t_end; ++t, ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
@@ -169,19 +171,20 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(XFORM ? xf_bar(s) : full_bar(s), ph);
           tc_fence_after();
-          const uint64_t da = desc_hi | (uint64_t)(a_base + (uint32_t)s * a_step);
-          const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)(p.b_resident ? kb : s) * b_step);
-          if (elect_one()) {
-            umma_bf16(tacc, da, db, idesc, kb != 0);
-            umma_bf16_acc(tacc, da + 2, db + 2, idesc);
-            umma_bf16_acc(tacc, da + 4, db + 4, idesc);
-            umma_bf16_acc(tacc, da + 6, db + 6, idesc);
+          // descriptors as {32-bit start-address word, constant high word}: the K-step advance is a 32-bit add
+          const uint32_t a_lo = a_base + (uint32_t)s * a_step;
+          const uint32_t b_lo = b_base + (uint32_t)(bres ? kb : s) * b_step;
+          if (leader) {
+            umma_bf16_lo(tacc, a_lo, b_lo, hi, idesc, kb != 0);
+            umma_bf16_lo(tacc, a_lo + 2, b_lo + 2, hi, idesc, true);
+            umma_bf16_lo(tacc, a_lo + 4, b_lo + 4, hi, idesc, true);
+            umma_bf16_lo(tacc, a_lo + 6, b_lo + 6, hi, idesc, true);
             umma_commit(empty_bar(s));
           }
           __syncwarp();
           if (++s == S) { s = 0; ph ^= 1u; }
         }
-        if (elect_one()) umma_commit(tfull_bar(buf));
+        if (leader) umma_commit(tfull_bar(buf));
         __syncwarp();
       }
     }
