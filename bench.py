@@ -163,6 +163,10 @@ def run_ours(args):
         torch.manual_seed(seed)
         gens.append(EnhancedGenerator(c, nb).to(dev))
     sty = MultiStyleStylizer(gens, precision=args.precision, micro_batch=args.micro_batch)
+    # per-launch CUDA-event breakdown (roofline): the same step with one stream and no graph replay, because launches
+    # inside a replayed graph cannot be bracketed by events and concurrent kernels of different styles share the SMs
+    sty_serial = MultiStyleStylizer(gens, precision=args.precision, micro_batch=args.micro_batch, style_streams=False,
+                                    use_graph=False)
     x_host = synth_images(B, H, W, seed=1234 + rank).pin_memory()
     x_dev = x_host.to(dev)
     out_dev = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
@@ -199,7 +203,8 @@ def run_ours(args):
         sampler.start()
     # inputs (64 x 512^2 fp32 = 201 MB) + the activations of each micro-batch exceed the 126 MB L2,
     # so nothing is L2-resident between timed iterations (no explicit flush needed).
-    ms_dev, launches, breakdown = timed(lambda: sty(x_dev, STYLE_W, out=out_dev), args.steps, args.warmup, prof=True)
+    ms_dev, launches, _ = timed(lambda: sty(x_dev, STYLE_W, out=out_dev), args.steps, args.warmup)
+    ms_serial, _, breakdown = timed(lambda: sty_serial(x_dev, STYLE_W, out=out_dev), args.steps, 1, prof=True)
     ms_e2e, _, _ = timed(lambda: (sty(x_host, STYLE_W, out_uint8=True, out=out_host), torch.cuda.current_stream().synchronize()),
                          max(2, args.steps // 2), 1)
     clocks = sampler.stop() if rank == 0 else None
@@ -213,7 +218,7 @@ def run_ours(args):
             "config": {"workload": f"batch stylisation {H}x{W}, batch {B} per GPU, 3 style weights {STYLE_W}, "
                                    f"c={c}/{nb}-block EnhancedGenerator, reference-faithful output blend = 3 generator "
                                    f"forwards per image ({3 * GEN_GFLOP_512 * (H * W) / 512 ** 2:.1f} GFLOP/image)",
-                       "global_batch": B * world, "micro_batch": args.micro_batch, "parallelism": f"image-sharded x{world}, no collective",
+                       "global_batch": B * world, "micro_batch": args.micro_batch, "schedule": f"style_streams={int(sty.style_streams)}, cuda_graph={int(sty.use_graph)}", "parallelism": f"image-sharded x{world}, no collective",
                        "l2": "inputs + per-micro-batch activations > 126 MB L2; no flush needed",
                        "weights": "random init (seeds 0,1,2), fp32 master, bf16 packed"},
             "gpu_launches": launches,
@@ -233,7 +238,9 @@ def run_ours(args):
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                                 "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",
-                                "launches_per_step": conv_launches, "ms_per_step": conv_ms}
+                                "launches_per_step": conv_launches, "ms_per_step": conv_ms,
+                                "measured_on": f"serialised pass of the same step (one stream, no graph replay, {ms_serial:.1f} ms per step): "
+                                               "launches inside a replayed graph cannot be bracketed by events"}
         in_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in ("msg_instnorm_apply", "msg_instnorm_stats")) / args.steps
         if in_ms > 0:
             in_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in ("msg_instnorm_apply", "msg_instnorm_stats")) // args.steps

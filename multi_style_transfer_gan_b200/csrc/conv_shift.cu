@@ -120,6 +120,8 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       kb_acc = !d.kb_first[lane];
     }
     const uint32_t a_base = sA >> 4;
+    const uint32_t hi = (uint32_t)(sw128_hi >> 32);
+    const bool leader = elect_one();          // one election for the whole kernel
     int s = 0;
     uint32_t ph = 0, lt = 0;
     mbar_wait(wres_bar, 0);
@@ -129,24 +131,24 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot);
       for (int kb = 0; kb < d.n_kblocks; ++kb) {
-        const uint64_t db = sw128_hi | (uint64_t)__shfl_sync(0xffffffffu, kb_b, kb);
+        const uint32_t b_lo = __shfl_sync(0xffffffffu, kb_b, kb);
         const uint32_t idesc = __shfl_sync(0xffffffffu, kb_idesc, kb);
         const uint32_t dcol = tacc + __shfl_sync(0xffffffffu, kb_col, kb);
         const uint32_t acc = __shfl_sync(0xffffffffu, kb_acc, kb);
-        const uint64_t da = sw128_hi | (uint64_t)(a_base + (uint32_t)s * (A_BYTES >> 4));
+        const uint32_t a_lo = a_base + (uint32_t)s * (A_BYTES >> 4);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (elect_one()) {
-          umma_bf16(dcol, da, db, idesc, acc);
-          umma_bf16(dcol, da + 2, db + 2, idesc, 1);
-          umma_bf16(dcol, da + 4, db + 4, idesc, 1);
-          umma_bf16(dcol, da + 6, db + 6, idesc, 1);
+        if (leader) {            // descriptors as {32-bit start-address word, constant high word}: 32-bit K-step adds
+          umma_bf16_lo(dcol, a_lo, b_lo, hi, idesc, acc != 0);
+          umma_bf16_lo(dcol, a_lo + 2, b_lo + 2, hi, idesc, true);
+          umma_bf16_lo(dcol, a_lo + 4, b_lo + 4, hi, idesc, true);
+          umma_bf16_lo(dcol, a_lo + 6, b_lo + 6, hi, idesc, true);
           umma_commit(empty_bar(s));
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
-      if (elect_one()) umma_commit(tfull_bar(buf));
+      if (leader) umma_commit(tfull_bar(buf));
       __syncwarp();
     }
   } else {

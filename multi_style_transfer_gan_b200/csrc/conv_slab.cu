@@ -86,7 +86,8 @@ __host__ __device__ constexpr int msb_taps_before(int dyi) {   // taps of one ch
   return n;
 }
 
-template <int MSBC>      // 0: generic program from the descriptor; 64 / 128: the MultiScaleBlock forward program of that width
+template <int MSBC>      // 0: generic program from the descriptor; 64 / 128: the MultiScaleBlock forward program of that width;
+                         // 7: the 7x7 input conv on the 8-channel image (pixel-pair K, all seven rows in one K block)
 __global__ void __launch_bounds__(NTHREADS_MAX, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const SlabParams p) {
@@ -220,7 +221,38 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int s = 0;
     uint32_t ph = 0, lt = 0;
     if (p.b_resident) mbar_wait(wres_bar, 0);
-    if constexpr (MSBC != 0) {
+    if constexpr (MSBC == 7) {
+      // ---- 7x7 input conv: 7 rows x 4 pixel-pair taps, one K block per tile, 28 MMAs of straight-line code --------
+      // (the generic loop broadcast per-tap operands with shuffles: ~195 cycles per MMA against 48 on the pipe)
+      const uint32_t a_hi = (uint32_t)(noswz_hi >> 32), a_lo0 = (uint32_t)noswz_hi;      // LBO lives in the low word
+      const uint32_t b_hi = (uint32_t)(sw128_hi >> 32);
+      const bool leader = elect_one();
+      const uint32_t a_base = (sA >> 4) + a_lo0, a_step = (uint32_t)p.a_bytes >> 4;
+      const uint32_t row_u = (uint32_t)(p.a_bytes / p.a_rows) >> 4;      // one input row of the slab, 16-byte units
+      const uint32_t tile_u = (uint32_t)tap_bytes >> 4;                 // one filter row's weight tile
+      const uint32_t b_base = sB >> 4;
+      for (int t = t_begin; t < t_end; t += tstep, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a0 = a_base + (uint32_t)s * a_step;
+        if (leader) {
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_bf16_lo2(tacc, a0 + (uint32_t)kh * row_u + (uint32_t)(2 * j), a_hi,
+                            b_base + (uint32_t)kh * tile_u + (uint32_t)(2 * j), b_hi, idesc, !(kh == 0 && j == 0));
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    } else if constexpr (MSBC != 0) {
       // ---- specialised straight-line issue: every tap operand is an immediate --------------------------------
       constexpr int CB = MSBC / 64, Q = MSBC / 4, TAPU = Q * 8;      // weight tile of one tap in 16-byte units
       const uint32_t hi = (uint32_t)(sw128_hi >> 32);
@@ -581,6 +613,9 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     }
   p.a_rows = 1;
   p.b_tiles = n_tiles_total;
+  // straight-line issue code for the programs known at compile time (MSG_SLAB_SPECIALISE=0: generic loop)
+  static const bool env_spec = [] { const char* e = getenv("MSG_SLAB_SPECIALISE"); return !(e && e[0] == '0'); }();
+  int spec = 0;
   if (d->pixel_pair_k && p.b_resident && d->n_kblocks > 1) {
     // Consecutive filter rows -> ONE K block: a single TMA box {8 ch, Ws, rows} brings every input row of the tile
     // (out-of-image rows zero-filled), the issuer runs all taps back to back and commits once, instead of one
@@ -597,6 +632,13 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
       p.d.kb_tap_begin[1] = d->n_taps;
     }
   }
+  if (env_spec && d->pixel_pair_k && p.a_rows == 7 && p.b_resident && d->n_taps == 28 && d->n_chains == 1) {
+    bool ok = true;                                   // conv7_in_program: row kh, taps sx = 2j - 3 on K slice j
+    for (int tp = 0; tp < 28; ++tp)
+      ok = ok && d->tap_sx[tp] == 2 * (tp & 3) - 3 && d->tap_kstep[tp] == (tp & 3) && d->tap_acc_col[tp] == 0 &&
+           d->kb_tap_begin[tp >> 2] == (tp & ~3) && d->kb_dy[tp >> 2] == (tp >> 2) - 3;
+    if (ok && d->halo == 3) spec = 7;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
   const int stage_bytes = p.a_bytes + p.b_bytes;
@@ -608,11 +650,12 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   // A second epilogue group (every other tile) is available (MSG_SLAB_EPI_GROUPS=2) but off by default: measured on
   // B200 the programs here are bound by shared-memory bandwidth (A re-read by every small-N MMA), not by the
   // epilogue's instruction stream, and the group's staging costs pipeline stages (MSB C=64: 0.78 -> 0.90 ms).
-  p.epi_groups = 1;
+  // The 7x7 input conv (28 MMAs per tile once its issue loop is straight-line code) IS bound by the epilogue's
+  // instruction stream (ncu: issuer waits on tempty 42 %, epilogue warps 86 % busy): second group, 0.54 -> 0.43 ms.
+  p.epi_groups = ((220 * 1024 - fixed_for(2)) / stage_bytes >= (spec == 7 ? 3 : 6)) ? 2 : 1;
   if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
   // straight-line issue code for the MultiScaleBlock forward programs (C = 64, 128)
-  static const bool env_spec = [] { const char* e = getenv("MSG_SLAB_SPECIALISE"); return !(e && e[0] == '0'); }();
-  const int spec = (!env_spec || p.a_mode == 0) ? 0 : is_msb_program<64>(d) ? 64 : is_msb_program<128>(d) ? 128 : 0;
+  if (spec == 0 && env_spec && p.a_mode != 0) spec = is_msb_program<64>(d) ? 64 : is_msb_program<128>(d) ? 128 : 0;
   // Two issuers split the taps by accumulator column slice (disjoint TMEM columns => no ordering between the two
   // instruction streams): slices sorted by tap count, each given to the less loaded issuer.  Programs with a single
   // slice (dgrad, 7x7 convs) and the pixel-pair / chunk-plane modes keep one issuer.
@@ -683,6 +726,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -693,6 +737,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   const int nthreads = 64 + 128 * p.epi_groups + (p.issuers == 2 ? 32 : 0);
   if (spec == 64) conv_slab_kernel<64><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
   else if (spec == 128) conv_slab_kernel<128><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (spec == 7) conv_slab_kernel<7><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
   else conv_slab_kernel<0><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
   return check_launch("conv_slab_kernel");
 }

@@ -271,6 +271,10 @@ class EnhancedGenerator(nn.Module):
         self.use_checkpointing = True
         self._checkpointing = True
 
+    def param_version(self):
+        """Identity + in-place version of every parameter (captured CUDA graphs are keyed on it)."""
+        return tuple((q.data_ptr(), q._version) for q in self.parameters())
+
     def set_precision(self, precision):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")

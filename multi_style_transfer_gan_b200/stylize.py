@@ -12,9 +12,11 @@ amortise the persistent kernels' ramp-up/tail and the small-plane launches, smal
 activation footprint); host input is staged through pinned memory on a copy stream so H2D of
 micro-batch i+1 overlaps the compute of micro-batch i.
 """
+import os
+
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def shard_range(num_images, rank, world_size):
@@ -25,7 +27,7 @@ def shard_range(num_images, rank, world_size):
 
 
 class MultiStyleStylizer:
-    def __init__(self, generators, precision="bf16", micro_batch=16):
+    def __init__(self, generators, precision="bf16", micro_batch=16, style_streams=None, use_graph=None):
         if not generators:
             raise ValueError("need at least one generator (one per style)")
         self.generators = list(generators)
@@ -35,6 +37,72 @@ class MultiStyleStylizer:
         self.micro_batch = int(micro_batch)
         self.device = next(self.generators[0].parameters()).device
         self._copy_stream = None
+        # The S forwards of a micro-batch are independent until the blend: each style runs on its own stream, so the
+        # HBM-bound kernels of one style (1x1 convs, IN apply) overlap the shared-memory / issue-bound ones of another
+        # (MultiScaleBlock branches, LocalAttention) and one style's kernel tails are filled by the next one's CTAs.
+        if style_streams is None:
+            style_streams = os.environ.get("MSG_STYLE_STREAMS", "1") == "1"
+        self.style_streams = bool(style_streams) and len(self.generators) > 1
+        self._streams = None
+        if use_graph is None:
+            use_graph = os.environ.get("MSG_STYLE_GRAPH", "1") == "1"
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+
+    def _forward_chunk(self, xi, weights, w_x, gain, clip, dst):
+        """All styles of one micro-batch + the blend into dst, enqueued on the current stream (and the style streams)."""
+        cur = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.style_streams:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(self.device) for _ in self.generators]
+            ready = torch.cuda.Event()
+            ready.record(cur)                     # xi staged, previous micro-batch's blend enqueued
+            ys, done = [], []
+            for g, st in zip(self.generators, self._streams):
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    y = g(xi)
+                    ev_s = torch.cuda.Event()
+                    ev_s.record(st)
+                if not capturing:                 # (inside a capture the graph's private pool orders reuse itself)
+                    xi.record_stream(st)
+                    y.record_stream(cur)
+                ys.append(y)
+                done.append(ev_s)
+            for ev_s in done:
+                cur.wait_event(ev_s)
+        else:
+            ys = [g(xi) for g in self.generators]
+        ops.blend_outputs(ys, weights, x=xi if w_x != 0.0 else None, w_x=w_x, gain=gain, clip=clip, out=dst)
+
+    def _replay(self, xi, weights, w_x, gain, clip, dst):
+        """CUDA-graph path: the ~210 launches of a micro-batch (S forwards + blend) are captured once per
+        (shape, blend parameters) and replayed, so the host cost of a micro-batch is one graph launch.  Weights are
+        read through the per-generator pack caches at capture time: `invalidate_graphs()` after changing them."""
+        key = (tuple(xi.shape), tuple(float(w) for w in weights), float(w_x), float(gain), clip, dst.dtype,
+               tuple(g.param_version() for g in self.generators))
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx = torch.empty_like(xi)
+            sd = torch.empty_like(dst)
+            sx.copy_(xi)
+            for _ in range(2):                    # warm-up outside capture: weight packs, function attributes, allocator
+                self._forward_chunk(sx, weights, w_x, gain, clip, sd)
+            torch.cuda.current_stream(self.device).synchronize()
+            gr = torch.cuda.CUDAGraph()
+            l0 = _lib.launches
+            with torch.cuda.graph(gr):
+                self._forward_chunk(sx, weights, w_x, gain, clip, sd)
+            ent = self._graphs[key] = (gr, sx, sd, _lib.launches - l0)
+        gr, sx, sd, n_launches = ent
+        sx.copy_(xi)
+        gr.replay()
+        _lib.launches += n_launches               # kernels inside the replayed graph (the launch counter is per C-ABI call)
+        dst.copy_(sd)
+
+    def invalidate_graphs(self):
+        self._graphs.clear()
 
     @torch.no_grad()
     def __call__(self, x, weights, w_x=0.0, gain=1.0, clip=None, out_uint8=False, out=None):
@@ -77,11 +145,13 @@ class MultiStyleStylizer:
             if ev is not None:
                 cur.wait_event(ev)
                 xi.record_stream(cur)
-            ys = [g(xi) for g in self.generators]
             dst = None if host_out else out[lo:hi]      # device result: the blend writes it in place
             if dst is None:
-                dst = torch.empty(ys[0].shape, device=self.device, dtype=out.dtype)
-            ops.blend_outputs(ys, weights, x=xi if w_x != 0.0 else None, w_x=w_x, gain=gain, clip=clip, out=dst)
+                dst = torch.empty((hi - lo,) + tuple(out.shape[1:]), device=self.device, dtype=out.dtype)
+            if self.use_graph:
+                self._replay(xi, weights, w_x, gain, clip, dst)
+            else:
+                self._forward_chunk(xi, weights, w_x, gain, clip, dst)
             if host_out:
                 out[lo:hi].copy_(dst, non_blocking=True)
         return out
