@@ -142,6 +142,9 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+CONV_DRAM_BYTES_PER_LAUNCH = 552.87e6   # profiles/r1_launch_list_summary.md (final code of round 1)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from multi_style_transfer_gan_b200 import _lib, ops, profiler
@@ -236,7 +239,10 @@ def run_ours(args):
             ach = flops / (conv_ms * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": "conv_tma_kernel + conv_slab_kernel + conv_shift_kernel (every conv / convT launch of the step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                                "frac": ach / pk["bf16_tflops_sustained"],
+                                # dram__bytes_read.sum + dram__bytes_write.sum per conv launch (average over the 128 conv launches
+                                # of the ncu window in profiles/r1_launches_final.csv, 16-image micro-batch at 512^2)
+                                "traffic": CONV_DRAM_BYTES_PER_LAUNCH if (H == 512 and args.micro_batch == 16 and c == 64) else None,
                                 "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",
                                 "launches_per_step": conv_launches, "ms_per_step": conv_ms,
                                 "measured_on": f"serialised pass of the same step (one stream, no graph replay, {ms_serial:.1f} ms per step): "
