@@ -79,6 +79,10 @@ __host__ __device__ constexpr MsbTap msb_tap(int dyi, int j) {
   const int b = ad == 1 ? 1 : ad == 2 ? 2 : 3;
   return MsbTap{(j - 1) * ad, b};
 }
+// taps per K block (slab.py: msb_max_taps).  Measured on B200 for C = 128 (streamed weights): splitting the 10-tap centre row
+// into 4 + 4 + 2 (4 pipeline stages of 33 KB instead of 2 of 57 KB, but two more slab loads per tile) is SLOWER, 0.585 ->
+// 0.626 ms per 16 images: the kernel moves ~24 B/clk/SM from L2 either way, i.e. it is bound by L2 -> SM bytes, not latency.
+__host__ __device__ constexpr int msb_maxt(int) { return 32; }   // = no split for C = 64 and C = 128
 __host__ __device__ constexpr int msb_first_dyi(int branch) { return branch == 0 ? 3 : branch == 1 ? 2 : branch == 2 ? 1 : 0; }
 __host__ __device__ constexpr int msb_taps_before(int dyi) {   // taps of one channel block in the K blocks before row dyi
   int n = 0;
@@ -255,6 +259,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else if constexpr (MSBC != 0) {
       // ---- specialised straight-line issue: every tap operand is an immediate --------------------------------
       constexpr int CB = MSBC / 64, Q = MSBC / 4, TAPU = Q * 8;      // weight tile of one tap in 16-byte units
+      constexpr int MAXT = msb_maxt(MSBC);
       const uint32_t hi = (uint32_t)(sw128_hi >> 32);
       const bool leader = elect_one();
       const uint32_t a_base = sA >> 4, a_step = (uint32_t)p.a_bytes >> 4;
@@ -269,25 +274,28 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int dyi = 0; dyi < 7; ++dyi) {
 #pragma unroll
           for (int cb = 0; cb < CB; ++cb) {
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const int tp0 = msb_taps_before(dyi) * CB + cb * msb_ntaps(dyi);     // program-order index of this K block's first tap
-            const uint32_t a0 = a_base + (uint32_t)s * a_step;
-            const uint32_t b0 = bres ? b_base + (uint32_t)(tp0 * TAPU) : b_base + (uint32_t)s * b_step;
-            if (leader) {
 #pragma unroll
-              for (int j = 0; j < msb_ntaps(dyi); ++j) {
-                const MsbTap tap = msb_tap(dyi, j);
-                const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
+            for (int j0 = 0; j0 < msb_ntaps(dyi); j0 += MAXT) {      // K blocks of at most MAXT taps (slab.py: msb_program)
+              mbar_wait(full_bar(s), ph);
+              tc_fence_after();
+              const int tp0 = msb_taps_before(dyi) * CB + cb * msb_ntaps(dyi) + j0;   // program-order index of this K block's first tap
+              const uint32_t a0 = a_base + (uint32_t)s * a_step;
+              const uint32_t b0 = bres ? b_base + (uint32_t)(tp0 * TAPU) : b_base + (uint32_t)s * b_step;
+              if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16_lo(tacc + (uint32_t)(tap.branch * Q), a0 + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
-                               b0 + (uint32_t)(j * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+                for (int j = j0; j < (j0 + MAXT < msb_ntaps(dyi) ? j0 + MAXT : msb_ntaps(dyi)); ++j) {
+                  const MsbTap tap = msb_tap(dyi, j);
+                  const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_lo(tacc + (uint32_t)(tap.branch * Q), a0 + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
+                                 b0 + (uint32_t)((j - j0) * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+                }
+                umma_commit(empty_bar(s));
               }
-              umma_commit(empty_bar(s));
+              __syncwarp();
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
-            __syncwarp();
-            if (++s == S) { s = 0; ph ^= 1u; }
           }
         }
         if (leader) umma_commit(tfull_bar(buf));
@@ -528,22 +536,21 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // does the descriptor hold exactly the compile-time MultiScaleBlock program of width C?
 template <int C>
 bool is_msb_program(const msg_slab_desc* d) {
-  constexpr int CB = C / 64, Q = C / 4;
-  if (d->Cin != C || d->Ntot != C || d->ncols != Q || d->halo != 4 || d->pixel_pair_k || d->n_chains != 1 ||
-      d->n_kblocks != 7 * CB || d->n_taps != 28 * CB)
+  constexpr int CB = C / 64, Q = C / 4, MAXT = msb_maxt(C);
+  if (d->Cin != C || d->Ntot != C || d->ncols != Q || d->halo != 4 || d->pixel_pair_k || d->n_chains != 1 || d->n_taps != 28 * CB)
     return false;
-  int tp = 0;
+  int tp = 0, kb = 0;
   for (int dyi = 0; dyi < 7; ++dyi)
-    for (int cb = 0; cb < CB; ++cb) {
-      const int kb = dyi * CB + cb;
-      if (d->kb_dy[kb] != msb_dy(dyi) || d->kb_cb[kb] != cb || d->kb_tap_begin[kb] != tp) return false;
-      for (int j = 0; j < msb_ntaps(dyi); ++j, ++tp) {
-        const MsbTap t = msb_tap(dyi, j);
-        if (d->tap_sx[tp] != t.sx || d->tap_acc_col[tp] != t.branch * Q) return false;
-        if (d->tap_first[tp] != (cb == 0 && j == 0 && dyi == msb_first_dyi(t.branch) ? 1 : 0)) return false;
+    for (int cb = 0; cb < CB; ++cb)
+      for (int j0 = 0; j0 < msb_ntaps(dyi); j0 += MAXT, ++kb) {
+        if (kb >= d->n_kblocks || d->kb_dy[kb] != msb_dy(dyi) || d->kb_cb[kb] != cb || d->kb_tap_begin[kb] != tp) return false;
+        for (int j = j0; j < msb_ntaps(dyi) && j < j0 + MAXT; ++j, ++tp) {
+          const MsbTap t = msb_tap(dyi, j);
+          if (d->tap_sx[tp] != t.sx || d->tap_acc_col[tp] != t.branch * Q) return false;
+          if (d->tap_first[tp] != (cb == 0 && j == 0 && dyi == msb_first_dyi(t.branch) ? 1 : 0)) return false;
+        }
       }
-    }
-  return d->kb_tap_begin[7 * CB] == tp;
+  return kb == d->n_kblocks && d->kb_tap_begin[kb] == tp;
 }
 
 }  // namespace

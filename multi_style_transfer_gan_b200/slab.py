@@ -40,12 +40,21 @@ class SlabProgram:
         d.kb_tap_begin[len(self.kblocks)] = tp
 
 
-def msb_program(C):
+def msb_max_taps(C):
+    """Taps per k-block: at most 64 KB of weight tiles per k-block (C = 64: no split, the weights stay resident; C = 128:
+    no split; C = 256: the 10-tap centre row is 8 + 2).  A finer split for C = 128 (4 + 4 + 2: twice the pipeline stages,
+    two more slab loads per tile) measured slower on B200 (0.585 -> 0.626 ms per 16 images): the kernel is bound by
+    L2 -> SM bytes, not by TMA latency.  csrc/conv_slab.cu: msb_maxt mirrors this for the straight-line issue code."""
+    return max(1, (64 * 1024) // ((C // 4) * 128))
+
+
+def msb_program(C, max_taps=None):
     """All four MultiScaleBlock branches; branch b writes accumulator columns [(b-1)C/4, bC/4)."""
     q = C // 4
     branches = [(1, 1), (3, 1), (3, 2), (3, 4)]   # (k, dilation) of branch1..4
     kblocks = []
-    max_taps = max(1, (64 * 1024) // (q * 128))          # keep a k-block's weight tiles <= 64 KB of smem
+    if max_taps is None:
+        max_taps = msb_max_taps(C)
     for dy in (-4, -2, -1, 0, 1, 2, 4):
         for cb in range(C // 64):
             taps = []
