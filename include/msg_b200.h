@@ -115,6 +115,11 @@ typedef struct {
   int dtype;
   int N, H, W, Ci_total, ci_off, Cin;
   int Co_total, co_off;
+  int out_stride;  /* 0 / 1: y is [N,H,W,Co_total].  2: output pixel (y, x) of the conv lands at row
+                      2y + out_off_h, column 2x + out_off_w of y [N,2H,2W,Co_total]: one sub-pixel phase
+                      of a 4x4 stride-2 transposed conv run as a 2x2 conv on its row slabs
+                      (enhanced_generator.py:120-121, 127-128).  bf16 NHWC output only.              */
+  int out_off_h, out_off_w;
   int Ntot;        /* accumulator columns (multiple of 16, <= 256)                                */
   int n_store;     /* leading columns actually written to y (<= Ntot)                             */
   int ncols;       /* columns per tap (multiple of 16)                                            */

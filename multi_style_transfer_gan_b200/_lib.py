@@ -33,7 +33,7 @@ SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS = 32, 128
 class SlabDesc(ctypes.Structure):
     """mirrors msg_slab_desc (include/msg_b200.h)"""
     _fields_ = [(n, c_int) for n in (
-        "dtype", "N", "H", "W", "Ci_total", "ci_off", "Cin", "Co_total", "co_off", "Ntot", "n_store", "ncols",
+        "dtype", "N", "H", "W", "Ci_total", "ci_off", "Cin", "Co_total", "co_off", "out_stride", "out_off_h", "out_off_w", "Ntot", "n_store", "ncols",
         "halo", "pixel_pair_k", "n_chains", "act")] + [("flags", c_uint), ("n_kblocks", c_int), ("n_taps", c_int),
         ("kb_dy", c_int * SLAB_MAX_KBLOCKS), ("kb_cb", c_int * SLAB_MAX_KBLOCKS),
         ("kb_tap_begin", c_int * (SLAB_MAX_KBLOCKS + 1)),

@@ -30,7 +30,8 @@ constexpr int BM = 128;
 constexpr int NTHREADS_MAX = 352;       // producer + MMA issuer A + up to two epilogue groups of four warps + MMA issuer B
 constexpr int STAGE_PITCH = 128 + 16;
 constexpr int EPI_STAGE = 4 * 32 * STAGE_PITCH;          // per epilogue group: four per-warp skewed staging tiles
-constexpr int EPI_RED = 16384 + 4 * 1056 * 4;            // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][33]
+constexpr int EPI_TR = 4 * 1056 * 4;                     // per epilogue group: transpose scratch [4][32][33] floats
+                                                         // (+ fp64 column sums [4][2][Ntot] = 64 * Ntot bytes: SlabParams::epi_red)
 
 
 struct SlabParams {
@@ -48,6 +49,9 @@ struct SlabParams {
   int segs;           // 128-pixel segments per image row
   int a_rows;         // pixel-pair mode: input rows per slab (consecutive filter rows fused into ONE K block)
   int b_tiles;        // weight tiles in w_slab (= taps, or filter rows in pixel-pair mode)
+  int epi_red;        // bytes of one epilogue group's reduction scratch: fp64 sums [4][2][Ntot] + transposes
+  int trows;          // output rows per tile (1, or 2 for the streamed-weight MSB program: the weight tiles of a K block then
+                      // serve 256 pixels, halving the weight bytes per pixel -- that kernel is bound by L2 -> SM bytes)
   int interleave;     // tile schedule: 0 = contiguous range per CTA, 1 = round-robin over the grid
   int epi_groups;     // 1: warps 2-5 drain both accumulator buffers; 2: warps 2-5 own buffer 0, warps 6-9 buffer 1
   int issuers;        // 1: warp 1 issues every MMA; 2: the taps are split between warp 1 and the last warp by ACCUMULATOR COLUMN
@@ -90,7 +94,8 @@ __host__ __device__ constexpr int msb_taps_before(int dyi) {   // taps of one ch
   return n;
 }
 
-template <int MSBC>      // 0: generic program from the descriptor; 64 / 128: the MultiScaleBlock forward program of that width;
+template <int MSBC, int TR>   // TR: output rows per tile (compile-time for the straight-line issue code)
+                         // MSBC 0: generic program from the descriptor; 64 / 128: the MultiScaleBlock forward program of that width;
                          // 7: the 7x7 input conv on the 8-channel image (pixel-pair K, all seven rows in one K block)
 __global__ void __launch_bounds__(NTHREADS_MAX, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -107,7 +112,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t sA = sB + (p.b_resident ? p.b_resident : S * p.b_bytes);
   const uint32_t sStage = (sA + S * p.a_bytes + 127u) & ~127u;
   const uint32_t sRed = sStage + G * EPI_STAGE;               // per group: per-warp column sums [4][2][256] + transpose scratch
-  const uint32_t sBias = sRed + G * EPI_RED;                  // bias staged once per CTA (Ntot <= 256 floats)
+  const uint32_t sBias = sRed + G * p.epi_red;                  // bias staged once per CTA (Ntot <= 256 floats)
   const uint32_t sBar = sBias + 1024;
   uint8_t* stage_gen = gen + (sStage - base);
   float* red = reinterpret_cast<float*>(gen + (sRed - base));
@@ -148,7 +153,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = d.N * d.H * p.segs;
+  const int Hy = d.H / TR;                        // tile rows per image
+  const int total_tiles = d.N * Hy * p.segs;
   // tile schedule: CTA-contiguous ranges (tstep = 1), or round-robin (tstep = grid): then all CTAs work on neighbouring
   // rows of the same image at any time, so every input row comes from DRAM once and its 7 re-reads (one per dy) hit L2
   const int tstep = p.interleave ? (int)gridDim.x : 1;
@@ -170,7 +176,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       bool wrapped = false;
       for (int t = t_begin; t < t_end; t += tstep) {
         const int seg = t % p.segs, ny = t / p.segs;
-        const int yrow = ny % d.H, img = ny / d.H;
+        const int yrow = (ny % Hy) * TR, img = ny / Hy;
         const int x0 = seg * BM - d.halo;
         for (int kb = 0; kb < d.n_kblocks; ++kb) {
           if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
@@ -269,7 +275,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int buf = lt & 1;
         if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(buf * MSBC);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * MSBC * TR);
+        const uint32_t row_u = (uint32_t)(p.Ws * 128) >> 4;                  // second output row: next slab row, next MSBC columns
 #pragma unroll
         for (int dyi = 0; dyi < 7; ++dyi) {
 #pragma unroll
@@ -283,13 +290,17 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               const uint32_t b0 = bres ? b_base + (uint32_t)(tp0 * TAPU) : b_base + (uint32_t)s * b_step;
               if (leader) {
 #pragma unroll
-                for (int j = j0; j < (j0 + MAXT < msb_ntaps(dyi) ? j0 + MAXT : msb_ntaps(dyi)); ++j) {
-                  const MsbTap tap = msb_tap(dyi, j);
-                  const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
+                for (int r = 0; r < TR; ++r) {
+                  const uint32_t ar = a0 + (uint32_t)r * row_u, dr = tacc + (uint32_t)(r * MSBC);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_lo(tacc + (uint32_t)(tap.branch * Q), a0 + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
-                                 b0 + (uint32_t)((j - j0) * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+                  for (int j = j0; j < (j0 + MAXT < msb_ntaps(dyi) ? j0 + MAXT : msb_ntaps(dyi)); ++j) {
+                    const MsbTap tap = msb_tap(dyi, j);
+                    const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      umma_bf16_lo(dr + (uint32_t)(tap.branch * Q), ar + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
+                                   b0 + (uint32_t)((j - j0) * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+                  }
                 }
                 umma_commit(empty_bar(s));
               }
@@ -306,7 +317,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int buf = lt & 1;
       if (lt >= 2) mbar_wait(tempty_bar(buf), ((lt >> 1) - 1) & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * TR * d.Ntot * d.n_chains);
       for (int kb = 0; kb < d.n_kblocks; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -318,26 +329,30 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           // swizzle is a function of the absolute smem address, so base_offset stays 0 (verified on B200)
           const uint32_t a0s = a0 >> 4, b0s = b0 >> 4;
           if (elect_one()) {
-            uint4 e = tap_tab[t0];
-            for (int tp = t0; tp < t1; ++tp) {
-              const uint4 nx = tap_tab[tp + 1 < t1 ? tp + 1 : tp];      // prefetch the next entry
-              if ((int)(e.w >> 1) != issuer) { e = nx; continue; }     // the other issuer's accumulator slice
-              e.w &= 1u;
-              const uint64_t da = sw128_hi | (uint64_t)(a0s + e.x);
-              const uint64_t db = sw128_hi | (uint64_t)(b0s + e.y);
-              const uint32_t dcol = tacc + e.z;
-              if (nch == 1) {
-                umma_bf16(dcol, da, db, idesc, !e.w);
-                umma_bf16(dcol, da + 2, db + 2, idesc, 1);
-                umma_bf16(dcol, da + 4, db + 4, idesc, 1);
-                umma_bf16(dcol, da + 6, db + 6, idesc, 1);
-              } else {
-                umma_bf16(dcol, da, db, idesc, !e.w);
-                umma_bf16(dcol + ch1, da + 2, db + 2, idesc, !e.w);
-                umma_bf16(dcol + ch2, da + 4, db + 4, idesc, !(e.w && nch > 2));
-                umma_bf16(dcol + ch3, da + 6, db + 6, idesc, !(e.w && nch > 2));
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {           // TR == 2: second output row = next slab row, next Ntot accumulator columns
+              const uint32_t ar = a0s + (uint32_t)r * ((uint32_t)(p.Ws * 128) >> 4), dr = tacc + (uint32_t)(r * d.Ntot);
+              uint4 e = tap_tab[t0];
+              for (int tp = t0; tp < t1; ++tp) {
+                const uint4 nx = tap_tab[tp + 1 < t1 ? tp + 1 : tp];      // prefetch the next entry
+                if ((int)(e.w >> 1) != issuer) { e = nx; continue; }     // the other issuer's accumulator slice
+                e.w &= 1u;
+                const uint64_t da = sw128_hi | (uint64_t)(ar + e.x);
+                const uint64_t db = sw128_hi | (uint64_t)(b0s + e.y);
+                const uint32_t dcol = dr + e.z;
+                if (nch == 1) {
+                  umma_bf16(dcol, da, db, idesc, !e.w);
+                  umma_bf16(dcol, da + 2, db + 2, idesc, 1);
+                  umma_bf16(dcol, da + 4, db + 4, idesc, 1);
+                  umma_bf16(dcol, da + 6, db + 6, idesc, 1);
+                } else {
+                  umma_bf16(dcol, da, db, idesc, !e.w);
+                  umma_bf16(dcol + ch1, da + 2, db + 2, idesc, !e.w);
+                  umma_bf16(dcol + ch2, da + 4, db + 4, idesc, !(e.w && nch > 2));
+                  umma_bf16(dcol + ch3, da + 6, db + 6, idesc, !(e.w && nch > 2));
+                }
+                e = nx;
               }
-              e = nx;
             }
           }
         } else if (d.pixel_pair_k) {
@@ -385,10 +400,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
     uint8_t* stage_w = stage_gen + grp * EPI_STAGE + q * (32 * STAGE_PITCH);
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
-    double* wsum = reinterpret_cast<double*>(red + grp * (EPI_RED / 4)) + q * 512;   // [2][256] running column sums of this warp (fp64 above the
+    const int WS = d.Ntot;                        // sums in [0, WS), sums of squares in [WS, 2 WS)
+    double* wsum = reinterpret_cast<double*>(red + grp * (p.epi_red / 4)) + q * 2 * WS;   // [2][256] running column sums of this warp (fp64 above the
                                                                // fixed-order 32-row fp32 partials: grouping-independent)
-    float* tr = red + grp * (EPI_RED / 4) + 4096 + q * 1056;   // [32][33] transpose scratch of this warp
-    for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
+    float* tr = red + grp * (p.epi_red / 4) + 4 * 4 * WS + q * 1056;   // [32][33] transpose scratch of this warp (after the 4 warps' fp64 sums)
+    for (int i = lane; i < 2 * WS; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1;
     auto flush_stats = [&]() {
@@ -396,8 +412,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int c = lane; c < cmax; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
           atomicAdd(st, wsum[c]);
-          atomicAdd(st + 1, wsum[256 + c]);
-          wsum[c] = 0.0; wsum[256 + c] = 0.0;
+          atomicAdd(st + 1, wsum[WS + c]);
+          wsum[c] = 0.0; wsum[WS + c] = 0.0;
         }
       }
       __syncwarp();
@@ -406,16 +422,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint32_t lt = 0;
     for (int t = t_begin + (G == 2 ? grp * tstep : 0); t < t_end; t += G * tstep, ++lt) {
       const int seg = t % p.segs, ny = t / p.segs;
-      const int yrow = ny % d.H, img = ny / d.H;
+      const int yrow0 = (ny % Hy) * TR, img = ny / Hy;
       const int buf = G == 2 ? grp : (int)(lt & 1);                      // accumulator buffer of this tile
       const uint32_t tf_parity = G == 2 ? (lt & 1) : ((lt >> 1) & 1);    // its (lt or lt/2)-th use
       const int xcol = seg * BM + row;
       const bool valid = xcol < d.W;
-      const int opix = (img * d.H + yrow) * d.W + (valid ? xcol : 0);
       if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
       mbar_wait(tfull_bar(buf), tf_parity);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot * d.n_chains) + ((uint32_t)(q * 32) << 16);
+      for (int rr = 0; rr < TR; ++rr) {
+      const int yrow = yrow0 + rr;
+      const int os = d.out_stride > 1 ? d.out_stride : 1;      // sub-pixel phase of a transposed conv: strided output
+      const int opix = ((img * d.H + yrow) * os + d.out_off_h) * (d.W * os) + (valid ? xcol : 0) * os + d.out_off_w;
+      const uint32_t tacc = tmem_base + (uint32_t)((buf * TR + rr) * d.Ntot * d.n_chains) + ((uint32_t)(q * 32) << 16);
       for (int cg = 0; cg < cmax; cg += 64) {
         const int ncol = (cmax - cg) < 64 ? (cmax - cg) : 64;
         __syncwarp();
@@ -432,7 +451,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int jj = 0; jj < 64; ++jj)
             if (jj < 32 || ncol > 32) v[jj] += u[jj];
         }
-        if (cg + 64 >= cmax) {
+        if (cg + 64 >= cmax && rr == TR - 1) {      // last read of this accumulator buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -461,8 +480,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
               for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
               __syncwarp();
-              wsum[cg + h * 32 + lane] += (double)cs;
-              wsum[256 + cg + h * 32 + lane] += (double)css;
+              if (cg + h * 32 + lane < WS) {
+                wsum[cg + h * 32 + lane] += (double)cs;
+                wsum[WS + cg + h * 32 + lane] += (double)css;
+              }
             }
           }
         }
@@ -521,6 +542,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (e < ncol) y[e] = __float2bfloat16_rn(v[e]);
         }
       }
+      }   // rr
     }
     if (do_stats) flush_stats();
   }
@@ -577,6 +599,9 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   MSG_REQUIRE(!d->pixel_pair_k || d->n_taps <= 32, MSG_ERR_SHAPE, "conv_slab: pixel-pair programs hold at most 32 taps");
   MSG_REQUIRE((((uintptr_t)x | (uintptr_t)w_slab) & 15) == 0, MSG_ERR_ALIGN, "conv_slab: operands must be 16-byte aligned");
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv_slab: stats buffer missing");
+  MSG_REQUIRE(d->out_stride == 0 || d->out_stride == 1 ||
+                  (d->out_stride == 2 && !(d->flags & MSG_CONV_OUT_NCHW_F32) && (unsigned)d->out_off_h < 2u && (unsigned)d->out_off_w < 2u),
+              MSG_ERR_SHAPE, "conv_slab: out_stride must be 1, or 2 with offsets in {0,1} and an NHWC bf16 output");
   EncodeTiledFn enc = get_encode();
   MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "conv_slab: cuTensorMapEncodeTiled unavailable");
 
@@ -646,23 +671,33 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
            d->kb_tap_begin[tp >> 2] == (tp & ~3) && d->kb_dy[tp >> 2] == (tp >> 2) - 3;
     if (ok && d->halo == 3) spec = 7;
   }
+  // straight-line issue code for the MultiScaleBlock forward programs (C = 64, 128)
+  if (spec == 0 && env_spec && p.a_mode != 0) spec = is_msb_program<64>(d) ? 64 : is_msb_program<128>(d) ? 128 : 0;
+  p.epi_red = 64 * d->Ntot + EPI_TR;
+  auto fixed_for = [&](int groups) {
+    return 128 + groups * (EPI_STAGE + p.epi_red) + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
+  };
+  // two output rows per tile where the weights are streamed (C = 128): one weight fetch serves 256 pixels
+  static const int env_trows = [] { const char* e = getenv("MSG_SLAB_TROWS"); return e ? atoi(e) : 0; }();
+  p.trows = ((spec == 128 || spec == 0) && p.a_mode != 0 && !d->pixel_pair_k && d->n_chains == 1 && !p.b_resident &&
+             4 * d->Ntot <= 512 && d->H % 2 == 0 && env_trows != 1 &&
+             2 * (2 * p.a_bytes + p.b_bytes) + fixed_for(1) <= 220 * 1024) ? 2 : 1;   // two double-row stages must fit
+  if (p.trows == 2) { p.a_rows = 2; p.a_bytes *= 2; }
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.trows * d->Ntot * d->n_chains) p.tmem_cols <<= 1;
+  MSG_REQUIRE(p.tmem_cols <= 512, MSG_ERR_SHAPE, "conv_slab: accumulators do not fit in TMEM");
   const int stage_bytes = p.a_bytes + p.b_bytes;
   static const int env_groups = [] { const char* e = getenv("MSG_SLAB_EPI_GROUPS"); return e ? atoi(e) : 0; }();
   static const int env_issuers = [] { const char* e = getenv("MSG_SLAB_ISSUERS"); return e ? atoi(e) : 0; }();
-  auto fixed_for = [&](int groups) {
-    return 128 + groups * (EPI_STAGE + EPI_RED) + 1024 + 256 + MSG_SLAB_MAX_TAPS * 16 + 1024 + p.b_resident;
-  };
   // A second epilogue group (every other tile) is available (MSG_SLAB_EPI_GROUPS=2) but off by default: measured on
   // B200 the programs here are bound by shared-memory bandwidth (A re-read by every small-N MMA), not by the
   // epilogue's instruction stream, and the group's staging costs pipeline stages (MSB C=64: 0.78 -> 0.90 ms).
   // The 7x7 input conv (28 MMAs per tile once its issue loop is straight-line code) IS bound by the epilogue's
   // instruction stream (ncu: issuer waits on tempty 42 %, epilogue warps 86 % busy): second group, 0.54 -> 0.43 ms.
-  p.epi_groups = ((220 * 1024 - fixed_for(2)) / stage_bytes >= (spec == 7 ? 3 : 6)) ? 2 : 1;
+  // Same for any light program (<= 64 MMAs per tile, e.g. a transposed-conv phase at N = 64).
+  const int mmas_per_tile = d->pixel_pair_k ? d->n_taps : 4 * d->n_taps * p.trows;
+  p.epi_groups = (mmas_per_tile <= 64 && (220 * 1024 - fixed_for(2)) / stage_bytes >= 3) ? 2 : 1;
   if (env_groups == 1 || env_groups == 2) p.epi_groups = env_groups;
-  // straight-line issue code for the MultiScaleBlock forward programs (C = 64, 128)
-  if (spec == 0 && env_spec && p.a_mode != 0) spec = is_msb_program<64>(d) ? 64 : is_msb_program<128>(d) ? 128 : 0;
   // Two issuers split the taps by accumulator column slice (disjoint TMEM columns => no ordering between the two
   // instruction streams): slices sorted by tap count, each given to the less loaded issuer.  Programs with a single
   // slice (dgrad, 7x7 convs) and the pixel-pair / chunk-plane modes keep one issuer.
@@ -696,7 +731,11 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     }
   }
   static const int env_il = [] { const char* e = getenv("MSG_SLAB_INTERLEAVE"); return e ? atoi(e) : -1; }();
-  p.interleave = env_il >= 0 ? env_il : 1;
+  // Contiguous ranges by default.  Measured on B200 (16 images): round-robin (MSG_SLAB_INTERLEAVE=1) removes the DRAM
+  // re-reads of the C = 64 MSB program (1.8 -> 0.6 GB) but not its time (shared-memory bound: 0.79 -> 0.80 ms), is neutral for
+  // C = 128 (0.50 -> 0.49 ms) and costs where an image has few tiles (statistics flushed with fp64 atomics every few tiles:
+  // transposed-conv phases 0.49 -> 0.82 ms, 7x7 input conv 0.40 -> 0.45 ms).
+  p.interleave = env_il >= 0 ? env_il : 0;
   const int fixed = fixed_for(p.epi_groups);
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -730,21 +769,25 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   int grid = sm_count();
-  const long long total = (long long)d->N * d->H * p.segs;
+  const long long total = (long long)d->N * (d->H / p.trows) * p.segs;
   MSG_REQUIRE(total < 0x7fffffffLL, MSG_ERR_SHAPE, "conv_slab: too many tiles");
   if (grid > total) grid = (int)total;
   const int nthreads = 64 + 128 * p.epi_groups + (p.issuers == 2 ? 32 : 0);
-  if (spec == 64) conv_slab_kernel<64><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
-  else if (spec == 128) conv_slab_kernel<128><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
-  else if (spec == 7) conv_slab_kernel<7><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
-  else conv_slab_kernel<0><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  if (spec == 64) conv_slab_kernel<64, 1><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (spec == 128 && p.trows == 2) conv_slab_kernel<128, 2><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (spec == 128) conv_slab_kernel<128, 1><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (spec == 7) conv_slab_kernel<7, 1><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else if (p.trows == 2) conv_slab_kernel<0, 2><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
+  else conv_slab_kernel<0, 1><<<grid, nthreads, smem, as_stream(stream)>>>(mapA, mapB, p);
   return check_launch("conv_slab_kernel");
 }

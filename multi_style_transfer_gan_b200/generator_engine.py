@@ -59,6 +59,9 @@ class GeneratorEngine:
         self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
         self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
         self._msb64_prog = slab.msb64_shift_program()
+        self._convT_prog = {s: slab.convT_phase_programs(self.inwidth[s], self.width[s]) for s in ("up1", "up2")
+                            if self.inwidth[s] % 64 == 0 and self.width[s] % 16 == 0}
+        self.convT_slab = os.environ.get("MSG_CONVT_SLAB", "1") == "1"
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
 
@@ -123,7 +126,18 @@ class GeneratorEngine:
         N = a_in.shape[0]
         dev = a_in.device
         st0 = ops.new_stats(N, C, dev)
-        y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
+        if (self.convT_slab and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
+                C % 16 == 0 and C * self.inwidth[s] <= 64 * 128 and a_in.shape[2] % 8 == 0):
+            # (weights of a phase resident in shared memory: 128 -> 64 measured 0.64 -> 0.49 ms per 16 images at 256^2;
+            #  with streamed weights, 256 -> 128, the per-tap TMA kernel is as fast: 0.36 vs 0.38 ms)
+            # transposed conv as four row-slab programs (each input row slab read once per phase for both horizontal taps)
+            progs = self._convT_prog[s]
+            wsl = self._slab_cached(P, (s, "convT_w"), [f"{s}.0.weight"],
+                                    lambda: slab.convT_phase_weight_slabs(progs, self._packed(P, f"{s}.0", "fwd", dtype), self.inwidth[s], C))
+            y0 = torch.empty((N, 2 * a_in.shape[1], 2 * a_in.shape[2], C), device=dev, dtype=dtype)
+            slab.convT_slab(progs, a_in, wsl, self._bias(P, f"{s}.0"), y0, stats=st0)
+        else:
+            y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
         wq = self._packed(P, f"{s}.3.qkv", "fwd", dtype)
         if not keep and self.fuse_in_norm and g[f"{s}.3.qkv"].fused_in_norm_ok(y0, wq):
             # inference: ReLU(IN(y0)) has ONE consumer, the 1x1 qkv conv (LocalAttention has no residual), so the

@@ -119,6 +119,49 @@ def msb_dgrad_weight_slab(prog, weights, dtype=torch.bfloat16):
     return torch.cat(rows, 0).to(dtype).contiguous()
 
 
+def convT_phase_programs(Cin, Cout):
+    """4x4 stride-2 pad-1 transposed conv (enhanced_generator.py:120-121, 127-128) = four sub-pixel phases, each a 2x2
+    conv of the input plane (ops.ConvGeom.forward: phase (ph, pw) has padding (1-ph, 1-pw) and writes output pixels
+    (2y+ph, 2x+pw)).  As a row-slab program a phase reads each input row slab ONCE for both horizontal taps: half the
+    L2 -> SM bytes of the per-tap implicit GEMM, which is what bounds these layers.  Returns [(ph, pw, program)]."""
+    progs = []
+    for ph in range(2):
+        for pw in range(2):
+            kblocks = []
+            for th in range(2):
+                for cb in range(Cin // 64):
+                    kblocks.append((th - (1 - ph), cb, [(tw - (1 - pw), 0, 0, (th, tw, cb)) for tw in range(2)]))
+            progs.append((ph, pw, SlabProgram(Cin, Cout, Cout, Cout, 1, False, kblocks)))
+    return progs
+
+
+def convT_phase_weight_slabs(progs, wp, Cin, Cout):
+    """wp: the packed phase weights of ops.ConvGeom('convT').pack_fwd, bf16 [4][Cout][2][2][Cin] flat ->
+    one [n_taps*Cout, 64] slab per phase in program order."""
+    w = wp.reshape(4, Cout, 2, 2, Cin)
+    out = []
+    for ph, pw, prog in progs:
+        rows = [w[ph * 2 + pw, :, th, tw, cb * 64:(cb + 1) * 64] for _, _, taps in prog.kblocks for _, _, _, (th, tw, cb) in taps]
+        out.append(torch.cat(rows, 0).contiguous())
+    return out
+
+
+def convT_slab(progs, x, w_slabs, bias, out, stats=None):
+    """x [N,H,W,Cin] bf16 -> out [N,2H,2W,Cout] bf16 (all four phases; statistics accumulated over the four launches)."""
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    for (ph, pw, prog), wsl in zip(progs, w_slabs):
+        d = SlabDesc()
+        d.dtype, d.N, d.H, d.W, d.Ci_total, d.ci_off = _lib.BF16, N, H, W, Ci_total, 0
+        prog.fill(d)
+        d.Co_total, d.co_off, d.act = out.shape[3], 0, ops.ACT_NONE
+        d.out_stride, d.out_off_h, d.out_off_w = 2, ph, pw
+        d.flags = _lib.CONV_STATS if stats is not None else 0
+        _lib.call("msg_conv_slab", ctypes.byref(d), ops._p(x), ops._p(wsl), ops._p(bias), ops._p(out), ops._p(stats),
+                  ops._stream())
+    return out
+
+
 def conv7_out_program(c):
     kblocks = []
     for kh in range(7):

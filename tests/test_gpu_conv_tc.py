@@ -115,6 +115,31 @@ def test_slab_msb_branches(C, H, W):
     assert_parity(st, st_ref, 3e-3, "stats")
 
 
+@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 64, 16, 128), (256, 128, 8, 64), (64, 32, 6, 40), (128, 64, 7, 136)])
+def test_slab_convT_phases(Cin, Cout, H, W):
+    """4x4 stride-2 transposed conv as four row-slab programs (strided output) == conv_transpose2d, incl. IN statistics;
+    covers resident and streamed weights, one and two output rows per tile, ragged widths."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(0)
+    N, dt = 2, torch.bfloat16
+    x = torch.randn(N, Cin, H, W, device=DEV).to(dt).float()
+    w = (torch.randn(Cin, Cout, 4, 4, device=DEV) * (1.0 / (Cin * 4) ** 0.5)).to(dt).float()
+    b = torch.randn(Cout, device=DEV)
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    g = ops.ConvGeom("convT", Cin, Cout, 4, 2, 1)
+    progs = slab.convT_phase_programs(Cin, Cout)
+    wsl = slab.convT_phase_weight_slabs(progs, g.pack_fwd(w, dt), Cin, Cout)
+    st = ops.new_stats(N, Cout, DEV)
+    y = torch.zeros(N, 2 * H, 2 * W, Cout, device=DEV, dtype=dt)
+    slab.convT_slab(progs, nhwc(x), wsl, b, y, stats=st)
+    assert_parity(nchw(y), ref, 1e-2, "convT phases")
+    st_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1)
+    assert_parity(st, st_ref, 3e-3, "stats")
+    # and against the per-tap implicit-GEMM kernel (same packed weights)
+    y2 = g.forward(nhwc(x), g.pack_fwd(w, dt), b)
+    assert_parity(y, y2.float(), 1e-2, "vs conv_tma phases")
+
+
 @pytest.mark.parametrize("c,H,W", [(64, 16, 128), (64, 8, 384), (128, 8, 128), (64, 24, 40)])
 def test_slab_output_conv(c, H, W):
     from multi_style_transfer_gan_b200 import ops, slab
