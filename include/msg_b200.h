@@ -168,6 +168,13 @@ typedef struct {
   int grp_col0[MSG_SHIFT_MAX_GROUPS], grp_span[MSG_SHIFT_MAX_GROUPS], grp_out_col0[MSG_SHIFT_MAX_GROUPS],
       grp_out_cols[MSG_SHIFT_MAX_GROUPS], grp_term_begin[MSG_SHIFT_MAX_GROUPS + 1];
   int term_shift[MSG_SHIFT_MAX_TERMS], term_col[MSG_SHIFT_MAX_TERMS];
+  /* Multi-row tiles (the kernel is bound by L2 -> SM slab bytes): a tile produces tile_rows (0 / 1: one) consecutive
+   * output rows; k-block kb with kb_same_slab[kb] != 0 re-uses the slab of k-block kb-1 (same input row, another
+   * output row's filter row, other accumulator columns); output group g belongs to output row y + grp_row[g].
+   * 7x7 conv with tile_rows = 2: 8 slabs per 2 rows instead of 14. */
+  int tile_rows;
+  int kb_same_slab[MSG_SHIFT_MAX_KBLOCKS];
+  int grp_row[MSG_SHIFT_MAX_GROUPS];
 } msg_shift_desc;
 int msg_conv_shift(const msg_shift_desc* d, const void* x, const void* w_rows, const float* bias, void* y,
                    double* stats, void* stream);

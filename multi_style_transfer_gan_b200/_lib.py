@@ -52,7 +52,8 @@ class ShiftDesc(ctypes.Structure):
         (n, c_int * SHIFT_MAX_KBLOCKS) for n in ("kb_dy", "kb_cb", "kb_col0", "kb_ncols", "kb_wrow", "kb_first")] + [
         (n, c_int * SHIFT_MAX_GROUPS) for n in ("grp_col0", "grp_span", "grp_out_col0", "grp_out_cols")] + [
         ("grp_term_begin", c_int * (SHIFT_MAX_GROUPS + 1)),
-        ("term_shift", c_int * SHIFT_MAX_TERMS), ("term_col", c_int * SHIFT_MAX_TERMS)]
+        ("term_shift", c_int * SHIFT_MAX_TERMS), ("term_col", c_int * SHIFT_MAX_TERMS),
+        ("tile_rows", c_int), ("kb_same_slab", c_int * SHIFT_MAX_KBLOCKS), ("grp_row", c_int * SHIFT_MAX_GROUPS)]
 
 
 _P = c_void_p

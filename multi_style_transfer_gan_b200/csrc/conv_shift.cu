@@ -81,7 +81,9 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = d.N * d.H * p.segs;
+  const int R = d.tile_rows > 1 ? d.tile_rows : 1;      // output rows per tile
+  const int Hy = (d.H + R - 1) / R;
+  const int total_tiles = d.N * Hy * p.segs;
   const int t_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
   const int t_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
@@ -95,9 +97,10 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       bool wrapped = false;
       for (int t = t_begin; t < t_end; ++t) {
         const int seg = t % p.segs, ny = t / p.segs;
-        const int yrow = ny % d.H, img = ny / d.H;
+        const int yrow = (ny % Hy) * R, img = ny / Hy;
         const int x0 = seg * p.Wv - d.halo;
         for (int kb = 0; kb < d.n_kblocks; ++kb) {
+          if (d.kb_same_slab[kb]) continue;                    // re-uses the previous k-block's slab
           if (wrapped) mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), A_BYTES);
           tma_load_4d(sA + s * A_BYTES, &mapA, full_bar(s), d.kb_cb[kb] * 64, x0, yrow + d.kb_dy[kb], img);
@@ -112,8 +115,10 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // Single-warp serial issue: every instruction per K block is on the critical path.  Lane kb keeps the
     // tile-invariant operands of K block kb (<= 32 K blocks) in registers; the loop broadcasts them with
     // independent shuffles; stage / phase are counted incrementally (no div/mod by the runtime stage count).
-    uint32_t kb_b = 0, kb_idesc = 0, kb_col = 0, kb_acc = 1;
+    uint32_t kb_b = 0, kb_idesc = 0, kb_col = 0, kb_acc = 1, kb_same = 0, kb_last = 1;
     if (lane < d.n_kblocks) {
+      kb_same = d.kb_same_slab[lane] != 0;                     // shares the slab (pipeline stage) of k-block lane-1
+      kb_last = lane + 1 >= d.n_kblocks || d.kb_same_slab[lane + 1] == 0;   // last user of its slab: releases the stage
       kb_b = (sB + (uint32_t)d.kb_wrow[lane] * 128u) >> 4;
       kb_idesc = idesc0 | ((uint32_t)(d.kb_ncols[lane] >> 3) << 17);
       kb_col = (uint32_t)d.kb_col0[lane];
@@ -135,18 +140,22 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const uint32_t idesc = __shfl_sync(0xffffffffu, kb_idesc, kb);
         const uint32_t dcol = tacc + __shfl_sync(0xffffffffu, kb_col, kb);
         const uint32_t acc = __shfl_sync(0xffffffffu, kb_acc, kb);
+        const uint32_t same = __shfl_sync(0xffffffffu, kb_same, kb);
+        const uint32_t last = __shfl_sync(0xffffffffu, kb_last, kb);
         const uint32_t a_lo = a_base + (uint32_t)s * (A_BYTES >> 4);
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+        if (!same) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+        }
         if (leader) {            // descriptors as {32-bit start-address word, constant high word}: 32-bit K-step adds
           umma_bf16_lo(dcol, a_lo, b_lo, hi, idesc, acc != 0);
           umma_bf16_lo(dcol, a_lo + 2, b_lo + 2, hi, idesc, true);
           umma_bf16_lo(dcol, a_lo + 4, b_lo + 4, hi, idesc, true);
           umma_bf16_lo(dcol, a_lo + 6, b_lo + 6, hi, idesc, true);
-          umma_commit(empty_bar(s));
+          if (last) umma_commit(empty_bar(s));
         }
         __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
+        if (last && ++s == S) { s = 0; ph ^= 1u; }
       }
       if (leader) umma_commit(tfull_bar(buf));
       __syncwarp();
@@ -176,11 +185,10 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint32_t lt = 0;
     for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int seg = t % p.segs, ny = t / p.segs;
-      const int yrow = ny % d.H, img = ny / d.H;
+      const int yrow = (ny % Hy) * R, img = ny / Hy;
       const int buf = lt & 1;
       const int xcol = seg * p.Wv + row;                      // output column of this thread (if row < Wv)
-      const bool valid = row < p.Wv && xcol < d.W;
-      const size_t opix = ((size_t)img * d.H + yrow) * d.W + (valid ? xcol : 0);
+      const bool col_ok = row < p.Wv && xcol < d.W;
       if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
       mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
       tc_fence_after();
@@ -208,6 +216,9 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int g = 0; g < d.n_groups; ++g) {
         const int oc = d.grp_out_cols[g];                     // <= 16
         const int oc0 = d.grp_out_col0[g];
+        const int orow = yrow + d.grp_row[g];                 // output row of this group (multi-row tiles)
+        const bool valid = col_ok && orow < d.H;
+        const size_t opix = ((size_t)img * d.H + (orow < d.H ? orow : 0)) * d.W + (col_ok ? xcol : 0);
         float o[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) o[c] = 0.f;
@@ -249,13 +260,15 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         } else if (d.act == MSG_ACT_TANH) {
 #pragma unroll
           for (int c = 0; c < 16; ++c)
-            if (c < oc) o[c] = tanhf(o[c]);
+            if (c < oc) asm("tanh.approx.f32 %0, %1;" : "=f"(o[c]) : "f"(o[c]));   // MUFU.TANH: 2^-11 rel. error, far below
+                                                                                    // the bf16 operands' noise; tanhf was ~25
+                                                                                    // instructions x 3 on an epilogue-bound kernel
         }
         if (valid) {
           if (nchw) {
             float* y = reinterpret_cast<float*>(p.y);
             const size_t plane = (size_t)d.H * d.W;
-            const size_t pp = (size_t)yrow * d.W + xcol;
+            const size_t pp = (size_t)orow * d.W + xcol;
 #pragma unroll
             for (int c = 0; c < 16; ++c)
               if (c < oc) y[((size_t)img * d.Co_total + d.co_off + oc0 + c) * plane + pp] = o[c];

@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS, ShiftDesc, SlabDesc
+from ._lib import SHIFT_MAX_KBLOCKS, SLAB_MAX_KBLOCKS, SLAB_MAX_TAPS, ShiftDesc, SlabDesc
 
 
 class SlabProgram:
@@ -226,19 +226,29 @@ def conv_slab(prog, x, w_slab, bias, out=None, co_off=0, stats=None, act=ops.ACT
 # "taps-as-N" programs (csrc/conv_shift.cu)
 # --------------------------------------------------------------------------------------------------
 class ShiftProgram:
-    def __init__(self, Cin, Ntot, n_out, halo, kblocks, groups):
-        """kblocks: [(dy, cb, col0, ncols, wrow)] (the first one must cover every accumulator column: it
-        overwrites, the others accumulate); groups: [(col0, span, out_col0, out_cols, [(shift, col), ...])]"""
+    def __init__(self, Cin, Ntot, n_out, halo, kblocks, groups, tile_rows=1):
+        """kblocks: [(dy, cb, col0, ncols, wrow)] or [(dy, cb, col0, ncols, wrow, first, same_slab)]: without explicit
+        flags the first k-block must cover every accumulator column (it overwrites, the others accumulate);
+        same_slab: re-use the slab of the previous k-block.
+        groups: [(col0, span, out_col0, out_cols, [(shift, col), ...])] or [..., row] (output row inside a multi-row tile)"""
         self.Cin, self.Ntot, self.n_out, self.halo, self.kblocks, self.groups = Cin, Ntot, n_out, halo, kblocks, groups
-        assert kblocks[0][2] == 0 and kblocks[0][3] == Ntot
+        self.tile_rows = tile_rows
+        if len(kblocks[0]) == 5:
+            assert kblocks[0][2] == 0 and kblocks[0][3] == Ntot
 
     def fill(self, d):
         d.Cin, d.Ntot, d.n_out, d.halo = self.Cin, self.Ntot, self.n_out, self.halo
         d.n_kblocks, d.n_groups = len(self.kblocks), len(self.groups)
-        for i, (dy, cb, col0, ncols, wrow) in enumerate(self.kblocks):
-            d.kb_dy[i], d.kb_cb[i], d.kb_col0[i], d.kb_ncols[i], d.kb_wrow[i], d.kb_first[i] = dy, cb, col0, ncols, wrow, int(i == 0)
+        d.tile_rows = self.tile_rows
+        for i, kb in enumerate(self.kblocks):
+            dy, cb, col0, ncols, wrow = kb[:5]
+            first, same = (kb[5], kb[6]) if len(kb) == 7 else (int(i == 0), 0)
+            d.kb_dy[i], d.kb_cb[i], d.kb_col0[i], d.kb_ncols[i], d.kb_wrow[i], d.kb_first[i] = dy, cb, col0, ncols, wrow, first
+            d.kb_same_slab[i] = same
         t = 0
-        for g, (col0, span, oc0, oc, terms) in enumerate(self.groups):
+        for g, grp in enumerate(self.groups):
+            col0, span, oc0, oc, terms = grp[:5]
+            d.grp_row[g] = grp[5] if len(grp) == 6 else 0
             d.grp_col0[g], d.grp_span[g], d.grp_out_col0[g], d.grp_out_cols[g], d.grp_term_begin[g] = col0, span, oc0, oc, t
             for shift, col in terms:
                 d.term_shift[t], d.term_col[t] = shift, col
@@ -247,12 +257,28 @@ class ShiftProgram:
         d.n_terms = t
 
 
-def conv7_out_shift_program(c):
-    """7x7 c->3 conv: per filter row ONE N=32 MMA (7 taps x 4 padded filters); 28*c/64 MMAs per tile."""
+def conv7_out_shift_program(c, tile_rows=2):
+    """7x7 c->3 conv: per filter row ONE N=32 MMA (7 taps x 4 padded filters); 28*c/64 MMAs per output row.
+    tile_rows = 2: a tile is two output rows; input row y+dy (dy = -3..4) is loaded ONCE and feeds filter row dy+3 of
+    output row y (accumulator columns [0,32)) and filter row dy+2 of row y+1 (columns [32,64)): 8 slabs per 2 rows
+    instead of 14 -- the kernel is bound by L2 -> SM slab bytes."""
     CB = c // 64
-    kblocks = [(kh - 3, cb, 0, 32, (kh * CB + cb) * 32) for kh in range(7) for cb in range(CB)]
-    groups = [(0, 28, 0, 3, [(kw, kw * 4) for kw in range(7)])]
-    return ShiftProgram(c, 32, 3, 3, kblocks, groups)
+    terms = [(kw, kw * 4) for kw in range(7)]
+    if tile_rows == 1 or 14 * CB > SHIFT_MAX_KBLOCKS:
+        kblocks = [(kh - 3, cb, 0, 32, (kh * CB + cb) * 32) for kh in range(7) for cb in range(CB)]
+        return ShiftProgram(c, 32, 3, 3, kblocks, [(0, 28, 0, 3, terms)])
+    kblocks, seen = [], set()
+    for dy in range(-3, 5):
+        for cb in range(CB):
+            same = 0
+            for r in (0, 1):
+                kh = dy + 3 - r
+                if 0 <= kh <= 6:
+                    kblocks.append((dy, cb, 32 * r, 32, (kh * CB + cb) * 32, int(r not in seen), same))
+                    seen.add(r)
+                    same = 1
+    groups = [(0, 28, 0, 3, terms, 0), (32, 28, 0, 3, terms, 1)]
+    return ShiftProgram(c, 64, 3, 3, kblocks, groups, tile_rows=2)
 
 
 def conv7_out_shift_weights(prog, w, dtype=torch.bfloat16):

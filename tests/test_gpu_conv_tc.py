@@ -203,6 +203,11 @@ def test_shift_output_conv(c, H, W):
     y = torch.empty(N, 3, H, W, device=DEV)
     slab.conv_shift(prog, nhwc(x), slab.conv7_out_shift_weights(prog, w), b, act=ops.ACT_TANH, nchw_out=y)
     assert_parity(y, torch.tanh(F.conv2d(x, w, b, padding=3)), 1e-2, "7x7 output conv + tanh (taps-as-N)")
+    # one output row per tile (14 slabs per 2 rows) gives the same result as the default two-row tiles (8 slabs)
+    prog1 = slab.conv7_out_shift_program(c, tile_rows=1)
+    y1 = torch.empty(N, 3, H, W, device=DEV)
+    slab.conv_shift(prog1, nhwc(x), slab.conv7_out_shift_weights(prog1, w), b, act=ops.ACT_TANH, nchw_out=y1)
+    assert_parity(y, y1, 1e-5, "two-row vs one-row tiles")
 
 
 # ---- tcgen05 wgrad (csrc/conv_wgrad_tc.cu) -----------------------------------------------------------
