@@ -94,6 +94,8 @@ class MultiStyleStylizer:
             l0 = _lib.launches
             with torch.cuda.graph(gr):
                 self._forward_chunk(sx, weights, w_x, gain, clip, sd)
+            while len(self._graphs) >= 8:         # stale keys (old parameter versions, other shapes): drop the oldest
+                self._graphs.pop(next(iter(self._graphs)))
             ent = self._graphs[key] = (gr, sx, sd, _lib.launches - l0)
         gr, sx, sd, n_launches = ent
         sx.copy_(xi)
