@@ -30,7 +30,7 @@ constexpr int BM = 128;
 constexpr int NTHREADS_MAX = 352;       // producer + MMA issuer A + up to two epilogue groups of four warps + MMA issuer B
 constexpr int STAGE_PITCH = 128 + 16;
 constexpr int EPI_STAGE = 4 * 32 * STAGE_PITCH;          // per epilogue group: four per-warp skewed staging tiles
-constexpr int EPI_TR = 4 * 1056 * 4;                     // per epilogue group: transpose scratch [4][32][33] floats
+constexpr int EPI_TR = 4 * 1088 * 4;                     // per epilogue group: transpose scratch [4][32][34] floats
                                                          // (+ fp64 column sums [4][2][Ntot] = 64 * Ntot bytes: SlabParams::epi_red)
 
 
@@ -403,7 +403,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int WS = d.Ntot;                        // sums in [0, WS), sums of squares in [WS, 2 WS)
     double* wsum = reinterpret_cast<double*>(red + grp * (p.epi_red / 4)) + q * 2 * WS;   // [2][256] running column sums of this warp (fp64 above the
                                                                // fixed-order 32-row fp32 partials: grouping-independent)
-    float* tr = red + grp * (p.epi_red / 4) + 4 * 4 * WS + q * 1056;   // [32][33] transpose scratch of this warp (after the 4 warps' fp64 sums)
+    float* tr = red + grp * (p.epi_red / 4) + 4 * 4 * WS + q * 1088;   // [32][34] transpose scratch of this warp (after the 4 warps' fp64 sums)
     for (int i = lane; i < 2 * WS; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1;
@@ -458,9 +458,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         if (p.bias != nullptr) {
           if (bias_in_smem) {
+            // packed f32x2 adds on 128-bit shared loads (columns >= ncol are never stored; sbias holds 256 floats)
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + cg);
 #pragma unroll
-            for (int jj = 0; jj < 64; ++jj)
-              if (jj < ncol) v[jj] += sbias[cg + jj];
+            for (int jj = 0; jj < 16; ++jj) {
+              const float4 b = b4[jj];
+              const float2 lo = __fadd2_rn(make_float2(v[4 * jj], v[4 * jj + 1]), make_float2(b.x, b.y));
+              const float2 hi2 = __fadd2_rn(make_float2(v[4 * jj + 2], v[4 * jj + 3]), make_float2(b.z, b.w));
+              v[4 * jj] = lo.x; v[4 * jj + 1] = lo.y; v[4 * jj + 2] = hi2.x; v[4 * jj + 3] = hi2.y;
+            }
           } else {
 #pragma unroll
             for (int jj = 0; jj < 64; ++jj)
@@ -471,14 +477,20 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 32 < ncol) {
-              // transpose this warp's 32 x 32 block through smem ([col][33]: conflict-free both ways); lane l
+              // transpose this warp's 32 x 32 block through smem ([col][34]: conflict-free both ways); lane l
               // then owns column l and sums its 32 rows (x and x^2) -- ~2x fewer instructions than shuffles
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) tr[jj * 33 + lane] = valid ? v[h * 32 + jj] : 0.f;
+              for (int jj = 0; jj < 32; ++jj) tr[jj * 34 + lane] = valid ? v[h * 32 + jj] : 0.f;
               __syncwarp();
-              float cs = 0.f, css = 0.f;
+              // packed f32x2: rows (2r, 2r+1) of this lane's column per LDS.64 (pitch 34: conflict-free both ways)
+              float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
+              for (int r = 0; r < 16; ++r) {
+                const float2 xv = *reinterpret_cast<const float2*>(&tr[lane * 34 + 2 * r]);
+                s2 = __fadd2_rn(s2, xv);
+                q2 = __ffma2_rn(xv, xv, q2);
+              }
+              const float cs = s2.x + s2.y, css = q2.x + q2.y;
               __syncwarp();
               if (cg + h * 32 + lane < WS) {
                 wsum[cg + h * 32 + lane] += (double)cs;

@@ -36,7 +36,7 @@ constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NTHREADS = 320;          // producer + MMA warp + up to two epilogue groups of four warps
 constexpr int NTHREADS_XF = 448;       // ... + four transform warps (fused input InstanceNorm)
-constexpr int EPI_FIXED = 16384 + 4 * 1056 * 4;  // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][33]
+constexpr int EPI_FIXED = 16384 + 4 * 1088 * 4;  // per epilogue group: fp64 column sums [4][2][256] + transpose scratch [4][32][34]
 constexpr int STAGE_PITCH = 128 + 16;   // manual flush: 64 bf16 columns per row + 16 B skew
 constexpr int STAGE_BYTES = 2 * BM * 128;   // two [128 rows x 64 cols] bf16 TMA-store buffers (SW128)
 
@@ -270,7 +270,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // order, everything above that is fp64, so an image's statistics do not depend on how tiles were grouped per CTA
     // (batch size, epilogue groups) beyond fp64 rounding
     double* wsum = reinterpret_cast<double*>(red + grp * (EPI_FIXED / 4)) + q * 512;
-    float* tr = red + grp * (EPI_FIXED / 4) + 4096 + q * 1056;            // [32][33] transpose scratch of this warp
+    float* tr = red + grp * (EPI_FIXED / 4) + 4096 + q * 1088;            // [32][34] transpose scratch of this warp
     for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
     __syncwarp();
     int stat_img = -1, stat_nt = -1, stat_cmax = 0;
@@ -326,9 +326,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         if (p.bias != nullptr) {
           if (bias_in_smem) {
+            // packed f32x2 adds on 128-bit shared loads: 16 LDS.128 + 32 FADD2 instead of 64 LDS + 64 FADD (the epilogue's
+            // instruction stream, not HBM, set the pace of the 1x1 convs).  Columns >= ncol are never stored.
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + co0 + cg);
 #pragma unroll
-            for (int jj = 0; jj < 64; ++jj)
-              if (jj < ncol) v[jj] += sbias[co0 + cg + jj];
+            for (int jj = 0; jj < 16; ++jj) {
+              const float4 b = b4[jj];
+              const float2 lo = __fadd2_rn(make_float2(v[4 * jj], v[4 * jj + 1]), make_float2(b.x, b.y));
+              const float2 hi2 = __fadd2_rn(make_float2(v[4 * jj + 2], v[4 * jj + 3]), make_float2(b.z, b.w));
+              v[4 * jj] = lo.x; v[4 * jj + 1] = lo.y; v[4 * jj + 2] = hi2.x; v[4 * jj + 3] = hi2.y;
+            }
           } else {
 #pragma unroll
             for (int jj = 0; jj < 64; ++jj)
@@ -341,14 +348,20 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 32 < ncol) {
-              // transpose this warp's 32 x 32 block through smem ([col][33]: conflict-free both ways); lane l
+              // transpose this warp's 32 x 32 block through smem ([col][34]: conflict-free both ways); lane l
               // then owns column l and sums its 32 rows (x and x^2) -- ~2x fewer instructions than shuffles
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) tr[jj * 33 + lane] = v[h * 32 + jj];
+              for (int jj = 0; jj < 32; ++jj) tr[jj * 34 + lane] = v[h * 32 + jj];
               __syncwarp();
-              float cs = 0.f, css = 0.f;
+              // packed f32x2: rows (2r, 2r+1) of this lane's column per LDS.64 (pitch 34: conflict-free both ways)
+              float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
+              for (int r = 0; r < 16; ++r) {
+                const float2 xv = *reinterpret_cast<const float2*>(&tr[lane * 34 + 2 * r]);
+                s2 = __fadd2_rn(s2, xv);
+                q2 = __ffma2_rn(xv, xv, q2);
+              }
+              const float cs = s2.x + s2.y, css = q2.x + q2.y;
               __syncwarp();
               wsum[cg + h * 32 + lane] += (double)cs;
               wsum[256 + cg + h * 32 + lane] += (double)css;
