@@ -146,8 +146,19 @@ in_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, long 
 // ---- apply, fast path (C power of two): activation / residual are template parameters, the channel
 // group of a thread is computed ONCE (no per-iteration 64-bit modulo), four independent 16-byte loads
 // are in flight per thread per iteration.
+template <typename T> __device__ __forceinline__ void raw_unpack(const uint4& t, float (&v)[Vec<T>::W]);
+template <> __device__ __forceinline__ void raw_unpack<float>(const uint4& t, float (&v)[4]) {
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+template <> __device__ __forceinline__ void raw_unpack<__nv_bfloat16>(const uint4& t, float (&v)[8]) { unpack8(t, v); }
+template <typename T> __device__ __forceinline__ uint4 raw_pack(const float (&v)[Vec<T>::W]);
+template <> __device__ __forceinline__ uint4 raw_pack<float>(const float (&v)[4]) {
+  return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+}
+template <> __device__ __forceinline__ uint4 raw_pack<__nv_bfloat16>(const float (&v)[8]) { return pack8(v); }
+
 template <typename T, int ACT, bool HAS_RES>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 3)
 in_apply_fast_kernel(const T* __restrict__ x, const double* __restrict__ stats, long long HW, int C,
                      const T* __restrict__ residual, int S, const float* __restrict__ gammas,
                      const float* __restrict__ betas, const float* __restrict__ w, T* __restrict__ y) {
@@ -180,29 +191,34 @@ in_apply_fast_kernel(const T* __restrict__ x, const double* __restrict__ stats, 
   const T* xb = x + base;
   const T* rb = HAS_RES ? residual + base : nullptr;
   T* yb = y + base;
+  // Loads stay RAW 16-byte vectors until they are consumed (unpacked floats would triple the registers that are live
+  // while the loads are in flight): 2 x U x 16 B in flight per thread at 3 CTAs per SM.
   for (long long v = v0; v < nvec; v += U * stride) {
-    float t[U][W], r[U][W];
+    uint4 tx[U], rx[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long vv = v + u * stride;
       if (vv < nvec) {
-        VecIO<W>::ld(xb + vv * W, t[u]);
-        if (HAS_RES) VecIO<W>::ld(rb + vv * W, r[u]);
+        tx[u] = *reinterpret_cast<const uint4*>(xb + vv * W);
+        if (HAS_RES) rx[u] = *reinterpret_cast<const uint4*>(rb + vv * W);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long vv = v + u * stride;
       if (vv < nvec) {
+        float t[W], r[W];
+        raw_unpack<T>(tx[u], t);
+        if (HAS_RES) raw_unpack<T>(rx[u], r);
 #pragma unroll
         for (int e = 0; e < W; ++e) {
-          float o = fmaf(t[u][e], scale[e], shift[e]);
+          float o = fmaf(t[e], scale[e], shift[e]);
           if (ACT == MSG_ACT_RELU) o = fmaxf(o, 0.f);
           else if (ACT == MSG_ACT_LRELU) o = o > 0.f ? o : 0.2f * o;
-          if (HAS_RES) o += r[u][e];
-          t[u][e] = o;
+          if (HAS_RES) o += r[e];
+          t[e] = o;
         }
-        VecIO<W>::st(yb + vv * W, t[u]);
+        *reinterpret_cast<uint4*>(yb + vv * W) = raw_pack<T>(t);
       }
     }
   }
@@ -355,8 +371,8 @@ int apply_impl(const T* x, const double* stats, int N, long long HW, int C, int 
                int S, const float* gammas, const float* betas, const float* w, T* y, cudaStream_t st) {
   if (fast_ok<T>(C, HW)) {
     const long long nvec = HW * C / Vec<T>::W;
-    static const int ctas_per_sm = [] { const char* e = getenv("MSG_IN_CTAS"); return e ? atoi(e) : 4; }();
-    long long want = ((long long)ctas_per_sm * sm_count() + N - 1) / N;   // ~4 CTAs per SM over the whole launch
+    static const int ctas_per_sm = [] { const char* e = getenv("MSG_IN_CTAS"); return e ? atoi(e) : 12; }();
+    long long want = ((long long)ctas_per_sm * sm_count() + N - 1) / N;   // CTAs per SM over the whole launch (3 resident at 80 registers; measured plateau from 8 up)
     long long maxb = (nvec + TPB * 4 - 1) / (TPB * 4);         // >= 4 vectors per thread
     if (want > maxb) want = maxb;
     if (want < 1) want = 1;
