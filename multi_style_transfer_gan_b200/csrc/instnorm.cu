@@ -248,15 +248,30 @@ in_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats,
       finalize_stats(st[0], st[1], inv_hw, mean[e], rstd[e]);
       sg[e] = 0.f; sgx[e] = 0.f;
     }
-    for (long long v = v0; v < nvec; v += stride) {
-      float t[W], g[W];
-      VecIO<Vec<T>::W>::ld(x + base + v * W, reinterpret_cast<float(&)[Vec<T>::W]>(t));
-      VecIO<Vec<T>::W>::ld(dy + base + v * W, reinterpret_cast<float(&)[Vec<T>::W]>(g));
+    constexpr int U = 4;          // 2 x U raw 16-byte loads in flight per thread (unpacked only when consumed)
+    for (long long v = v0; v < nvec; v += U * stride) {
+      uint4 tx[U], gx[U];
 #pragma unroll
-      for (int e = 0; e < W; ++e) {
-        float xh = (t[e] - mean[e]) * rstd[e];
-        float gg = g[e] * act_grad_from_pre(xh, act);
-        sg[e] += gg; sgx[e] = fmaf(gg, xh, sgx[e]);
+      for (int u = 0; u < U; ++u) {
+        const long long vv = v + u * stride;
+        if (vv < nvec) {
+          tx[u] = *reinterpret_cast<const uint4*>(x + base + vv * W);
+          gx[u] = *reinterpret_cast<const uint4*>(dy + base + vv * W);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v + u * stride < nvec) {
+          float t[Vec<T>::W], g[Vec<T>::W];
+          raw_unpack<T>(tx[u], t);
+          raw_unpack<T>(gx[u], g);
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            float xh = (t[e] - mean[e]) * rstd[e];
+            float gg = g[e] * act_grad_from_pre(xh, act);
+            sg[e] += gg; sgx[e] = fmaf(gg, xh, sgx[e]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -309,6 +324,46 @@ in_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats,
   const long long stride = (long long)gridDim.x * TPB;
   long long v0 = (long long)blockIdx.x * TPB + threadIdx.x;
   float mean[W], rstd[W], mg[W], mgx[W];
+  if constexpr (FAST) {
+    // channel group of a thread is loop-invariant (stride * W is a multiple of C); 2 x U raw loads in flight per thread
+    const int c0 = (int)((v0 * W) % C);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const double* st = stats + ((size_t)n * C + c0 + e) * 2;
+      finalize_stats(st[0], st[1], inv_hw, mean[e], rstd[e]);
+      const double* sc = scratch + ((size_t)n * C + c0 + e) * 2;
+      mg[e] = (float)(sc[0] * inv_hw); mgx[e] = (float)(sc[1] * inv_hw);
+    }
+    constexpr int U = 4;
+    for (long long v = v0; v < nvec; v += U * stride) {
+      uint4 tx[U], gx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long vv = v + u * stride;
+        if (vv < nvec) {
+          tx[u] = *reinterpret_cast<const uint4*>(x + base + vv * W);
+          gx[u] = *reinterpret_cast<const uint4*>(dy + base + vv * W);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long vv = v + u * stride;
+        if (vv < nvec) {
+          float t[Vec<T>::W], g[Vec<T>::W];
+          raw_unpack<T>(tx[u], t);
+          raw_unpack<T>(gx[u], g);
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            float xh = (t[e] - mean[e]) * rstd[e];
+            float gg = g[e] * act_grad_from_pre(xh, act);
+            t[e] = rstd[e] * (gg - mg[e] - xh * mgx[e]);
+          }
+          *reinterpret_cast<uint4*>(dx + base + vv * W) = raw_pack<T>(t);
+        }
+      }
+    }
+    return;
+  }
   int c_cached = -1;
   for (long long v = v0; v < nvec; v += stride) {
     int c0 = (int)((v * W) % C);
@@ -372,7 +427,12 @@ int apply_impl(const T* x, const double* stats, int N, long long HW, int C, int 
   if (fast_ok<T>(C, HW)) {
     const long long nvec = HW * C / Vec<T>::W;
     static const int ctas_per_sm = [] { const char* e = getenv("MSG_IN_CTAS"); return e ? atoi(e) : 12; }();
-    long long want = ((long long)ctas_per_sm * sm_count() + N - 1) / N;   // CTAs per SM over the whole launch (3 resident at 80 registers; measured plateau from 8 up)
+    // CTAs per SM over the whole launch (3 resident at 80 registers; measured plateau from 8 up on 537 MB tensors), but
+    // at least 32 vectors per thread: every thread pays an fp64 statistics finalisation for its 8 channels up front
+    long long total_ctas = (long long)ctas_per_sm * sm_count();
+    const long long by_work = ((long long)N * nvec) / (TPB * 32);
+    if (total_ctas > by_work) total_ctas = by_work > 4LL * sm_count() ? by_work : 4LL * sm_count();
+    long long want = (total_ctas + N - 1) / N;
     long long maxb = (nvec + TPB * 4 - 1) / (TPB * 4);         // >= 4 vectors per thread
     if (want > maxb) want = maxb;
     if (want < 1) want = 1;
