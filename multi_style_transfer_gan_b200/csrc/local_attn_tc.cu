@@ -39,7 +39,7 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
   uint8_t* os = sm + 2 * BUF;                 // [16][PITCH] output tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wpr = W / 4, wpi = (H / 4) * wpr;
-  const long long nwin = (long long)N * wpi;
+  const int nwin = N * wpi;                   // < 2^31 (checked on the host): 32-bit window arithmetic, no 64-bit div/mod per window
 
   // the (pixel, chunk) -> (smem, global) mapping of this thread's copies is window-independent: compute once
   uint32_t c_dst[NCHUNK];
@@ -57,10 +57,11 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
       c_src[i] = 0;
     }
   }
-  auto issue_load = [&](long long wi, int b) {
-    const int n = (int)(wi / wpi);
-    const int r = (int)(wi - (long long)n * wpi);
-    const int h0 = (r / wpr) * 4, w0 = (r % wpr) * 4;
+  auto issue_load = [&](int wi, int b) {
+    const int n = wi / wpi;
+    const int r = wi - n * wpi;
+    const int rr = r / wpr;
+    const int h0 = rr * 4, w0 = (r - rr * wpr) * 4;
     const uint32_t dst0 = s_u32(bufs + b * BUF);
     const __nv_bfloat16* src0 = qkv + (((size_t)n * H + h0) * W + w0) * (3 * C);
 #pragma unroll
@@ -69,11 +70,11 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  long long wi = blockIdx.x;
+  int wi = blockIdx.x;
   if (wi < nwin) issue_load(wi, 0);
   int b = 0;
   for (; wi < nwin; wi += gridDim.x, b ^= 1) {
-    const long long nxt = wi + gridDim.x;
+    const int nxt = wi + (int)gridDim.x;
     if (nxt < nwin) {
       issue_load(nxt, b ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -192,9 +193,10 @@ local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, in
     }
     __syncthreads();
     {
-      const int n = (int)(wi / wpi);
-      const int r = (int)(wi - (long long)n * wpi);
-      const int h0 = (r / wpr) * 4, w0 = (r % wpr) * 4;
+      const int n = wi / wpi;
+      const int r = wi - n * wpi;
+      const int rr = r / wpr;
+      const int h0 = rr * 4, w0 = (r - rr * wpr) * 4;
       for (int c = tid; c < P16 * CH; c += LT_THREADS) {
         const int p = c / CH, off = c - p * CH;
         uint4 val = *reinterpret_cast<const uint4*>(os + p * PITCH + off * 16);
@@ -212,6 +214,7 @@ int launch_impl(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* ou
   cudaError_t e = cudaFuncSetAttribute(local_attn_fwd_tc_kernel<C, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "local_attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const long long nwin = (long long)N * (H / 4) * (W / 4);
+  MSG_REQUIRE(nwin + 64LL * 1024 < 0x7fffffffLL, MSG_ERR_SHAPE, "local_attn_tc: too many windows");
   const int per_sm = C >= 256 ? 3 : (C >= 128 ? 4 : 8);   // resident CTAs per SM (smem / register limits)
   long long grid = (long long)per_sm * sm_count();
   if (grid > nwin) grid = nwin;
