@@ -22,6 +22,7 @@
 // (128 % Wg == 0 and Hg % (128/Wg) == 0).  Everything else takes the gather kernel (conv_tc.cu) or
 // the SIMT engine.  Same descriptor semantics as include/msg_b200.h.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -228,19 +229,40 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         mbar_wait(full_bar(s), ph);
         uint8_t* tile = gen + (sA - base) + s * A_BYTES + rbase * 128 + pchunk * 16;
+        if (d.in_act == MSG_ACT_RELU || d.in_act == MSG_ACT_NONE) {
+          // packed path: two fmaf per FFMA2 (same roundings as the apply kernel's fmaf), bf16 RN pack, ReLU as a packed bf16
+          // max AFTER rounding (rounding is monotone and keeps 0, so max(rn(o), 0) == rn(max(o, 0)) up to the sign of zero)
+          const bool relu = d.in_act == MSG_ACT_RELU;
+          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4* ptr = reinterpret_cast<uint4*>(tile + i * (16 * 128));
-          float v[8];
-          unpack8(*ptr, v);
+          for (int i = 0; i < 8; ++i) {
+            uint4* ptr = reinterpret_cast<uint4*>(tile + i * (16 * 128));
+            uint4 raw = *ptr;
+            uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float o = fmaf(v[e], sc[e], sh[e]);
-            if (d.in_act == MSG_ACT_RELU) o = fmaxf(o, 0.f);
-            else if (d.in_act == MSG_ACT_LRELU) o = o > 0.f ? o : 0.2f * o;
-            v[e] = o;
+            for (int j = 0; j < 4; ++j) {
+              const float2 x2 = make_float2(__uint_as_float(w4[j] << 16), __uint_as_float(w4[j] & 0xffff0000u));
+              const float2 o2 = __ffma2_rn(x2, make_float2(sc[2 * j], sc[2 * j + 1]), make_float2(sh[2 * j], sh[2 * j + 1]));
+              __nv_bfloat162 pk = __floats2bfloat162_rn(o2.x, o2.y);
+              if (relu) pk = __hmax2(pk, zero2);
+              w4[j] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            *ptr = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
-          *ptr = pack8(v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4* ptr = reinterpret_cast<uint4*>(tile + i * (16 * 128));
+            float v[8];
+            unpack8(*ptr, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float o = fmaf(v[e], sc[e], sh[e]);
+              o = o > 0.f ? o : 0.2f * o;
+              v[e] = o;
+            }
+            *ptr = pack8(v);
+          }
         }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
