@@ -33,6 +33,29 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, i
     y[idx] = from_f<T>(v);
   }
 }
+// fast path: one padded pixel = ONE 16-byte vector (bf16: Cp = 8, fp32: Cp = 4).  One thread per pixel: C coalesced
+// plane reads, one coalesced 16-byte store (the element-per-thread kernel above moved 117 MB in 0.18 ms = 0.64 TB/s).
+template <typename T>
+__global__ void nchw_to_nhwc_vec_kernel(const float* __restrict__ x, int N, int C, long long HW, T* __restrict__ y) {
+  constexpr int Cp = 16 / (int)sizeof(T);
+  const long long total = (long long)N * HW;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long n = pix / HW, p = pix - n * HW;
+    const float* src = x + (size_t)n * C * HW + p;
+    float v[Cp];
+#pragma unroll
+    for (int c = 0; c < Cp; ++c) v[c] = c < C ? src[(size_t)c * HW] : 0.f;
+    if constexpr (sizeof(T) == 2) {
+      float v8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v8[c] = v[c];
+      *reinterpret_cast<uint4*>(y + pix * Cp) = pack8(v8);
+    } else {
+      *reinterpret_cast<float4*>(y + pix * Cp) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int N, int C, int H, int W, int Cp,
                                     float* __restrict__ y) {
@@ -344,6 +367,14 @@ extern "C" int msg_nchw_to_nhwc(int dtype, const float* x, int N, int C, int H, 
                                 void* y, void* stream) {
   MSG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C, MSG_ERR_SHAPE, "nchw_to_nhwc: bad shape");
   long long total = (long long)N * H * W * Cp;
+  if (((dtype == MSG_BF16 && Cp == 8) || (dtype == MSG_F32 && Cp == 4)) && (((uintptr_t)y) & 15) == 0) {
+    const long long pixels = (long long)N * H * W;
+    if (dtype == MSG_BF16)
+      nchw_to_nhwc_vec_kernel<__nv_bfloat16><<<ew_blocks(pixels), EW_TPB, 0, as_stream(stream)>>>(x, N, C, (long long)H * W, (__nv_bfloat16*)y);
+    else
+      nchw_to_nhwc_vec_kernel<float><<<ew_blocks(pixels), EW_TPB, 0, as_stream(stream)>>>(x, N, C, (long long)H * W, (float*)y);
+    return check_launch("nchw_to_nhwc_vec_kernel");
+  }
   DISPATCH_DTYPE(dtype, "nchw_to_nhwc", (nchw_to_nhwc_kernel<T><<<ew_blocks(total), EW_TPB, 0, as_stream(stream)>>>(x, N, C, H, W, Cp, (T*)y)));
   return check_launch("nchw_to_nhwc_kernel");
 }
