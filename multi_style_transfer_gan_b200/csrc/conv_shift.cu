@@ -13,6 +13,9 @@
 //
 // Pipeline: warp 0 TMA producer (weights resident in smem, loaded once; one 128B-swizzled slab box per
 // k-block), warp 1 MMA issuer (warp-uniform loop, elected lane), warps 2-5 epilogue, double-buffered TMEM.
+// Multi-row tiles (msg_shift_desc::tile_rows, kb_same_slab, grp_row): the kernel moves ~24 B/clk/SM of slabs from L2, its
+// ceiling, so a tile of two output rows loads each input row ONCE and feeds it to both rows' filter rows (7x7 conv: 8
+// slab loads per 2 rows instead of 14); the output conv's tanh is MUFU.TANH (the epilogue sets the pace after that).
 #include <cuda.h>
 #include <stdlib.h>
 

@@ -16,6 +16,19 @@
 //
 // Pipeline = conv_tma.cu's: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue, smem ring of
 // slabs, double-buffered TMEM accumulators, persistent CTAs (one per SM).
+//
+// What bounds these kernels was measured (profiles/r1_mma_rate_microbench.md, r1_conv_slab_msb_ncu.md) and shaped the
+// variants below:
+//   * an M=128, K=16 tcgen05.mma costs ~39-45 cycles however small N is (its 4 KB A operand is re-read from shared memory),
+//     and one issuing thread must stay under ~4 instructions per MMA: the programs known at compile time (MultiScaleBlock
+//     at C = 64 / 128, 7x7 input conv) are template instantiations whose issue loop is straight-line code with immediate
+//     operands and {32-bit address word, constant high word} descriptors; the generic loop serves everything else
+//     (optionally split between two issuing warps by accumulator column slice);
+//   * per-CTA-distinct TMA traffic saturates at ~24 B/clk/SM: programs with streamed weights take TWO output rows per tile
+//     (template parameter TR), so a weight fetch serves 256 pixels; the four sub-pixel phases of a 4x4 stride-2 transposed
+//     conv run as 2x2 programs with a strided output (out_stride = 2), each input row slab serving both horizontal taps;
+//   * a second epilogue group (every other tile) where the epilogue's instruction stream is the bottleneck (7x7 input conv,
+//     transposed-conv phases); bias adds and column statistics use packed f32x2 arithmetic.
 #include <cuda.h>
 #include <stdlib.h>
 
