@@ -1,8 +1,8 @@
 // "Taps-as-N" row-slab convolution (sm_100a, bf16): stride-1 same-size convs whose per-tap N is tiny.
 //
-// A tcgen05.mma with M=128, K=16 costs ~90 cycles on B200 almost independently of N when N <= 64
-// (measured: the A-operand fetch dominates), so issuing one N=16 MMA per filter tap (conv_slab.cu)
-// leaves the tensor core ~10x under-used.  Here ALL taps that share an input-row slab are ONE MMA:
+// A tcgen05.mma with M=128, K=16 costs ~39-45 cycles on B200 whatever N is when N <= 64 (tools/mma_rate.cu: the 4 KB
+// A-operand read from shared memory dominates; ~90 with the generic issue loop around it), so issuing one N=16 MMA
+// per filter tap (conv_slab.cu) leaves the tensor core ~5-10x under-used.  Here ALL taps that share an input-row slab are ONE MMA:
 // the slab is the UNSHIFTED A operand [128 slab pixels x 64 ch], the taps' filters are stacked along N
 // (7 taps x 4 padded filters = 32 columns for the 7x7 output conv; 1 + 3x3 (branch, sx) column groups
 // of 16 = 160 columns for the MultiScaleBlock at C=64), giving partial products
