@@ -76,12 +76,12 @@ class MultiStyleStylizer:
             ys = [g(xi) for g in self.generators]
         ops.blend_outputs(ys, weights, x=xi if w_x != 0.0 else None, w_x=w_x, gain=gain, clip=clip, out=dst)
 
-    def _replay(self, xi, weights, w_x, gain, clip, dst):
+    def _replay(self, xi, weights, w_x, gain, clip, dst, pver=None):
         """CUDA-graph path: the ~210 launches of a micro-batch (S forwards + blend) are captured once per
         (shape, blend parameters) and replayed, so the host cost of a micro-batch is one graph launch.  Weights are
         read through the per-generator pack caches at capture time: `invalidate_graphs()` after changing them."""
         key = (tuple(xi.shape), tuple(float(w) for w in weights), float(w_x), float(gain), clip, dst.dtype,
-               tuple(g.param_version() for g in self.generators))
+               pver if pver is not None else tuple(g.param_version() for g in self.generators))
         ent = self._graphs.get(key)
         if ent is None:
             sx = torch.empty_like(xi)
@@ -126,6 +126,7 @@ class MultiStyleStylizer:
         if host_in and self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         chunks = [(lo, min(lo + mb, B)) for lo in range(0, B, mb)]
+        pver = tuple(g.param_version() for g in self.generators) if self.use_graph else None   # once per call, not per chunk
         staged = {}
 
         def stage(i):
@@ -151,7 +152,7 @@ class MultiStyleStylizer:
             if dst is None:
                 dst = torch.empty((hi - lo,) + tuple(out.shape[1:]), device=self.device, dtype=out.dtype)
             if self.use_graph:
-                self._replay(xi, weights, w_x, gain, clip, dst)
+                self._replay(xi, weights, w_x, gain, clip, dst, pver)
             else:
                 self._forward_chunk(xi, weights, w_x, gain, clip, dst)
             if host_out:
