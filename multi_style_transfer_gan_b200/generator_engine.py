@@ -30,6 +30,23 @@ def _pad_dim(t, dim, to):
     return F.pad(t, pad)
 
 
+class _StatsArena:
+    """All InstanceNorm statistics buffers ([N, C, 2] fp64 raw sums) of one encode / decode call come from ONE zeroed
+    allocation: one fill launch instead of one per normalised tensor (13 per forward)."""
+
+    def __init__(self, N, channels_total, device):
+        self.buf = torch.zeros(N * channels_total * 2, device=device, dtype=torch.float64)
+        self.N, self.pos = N, 0
+
+    def take(self, C):
+        n = self.N * C * 2
+        if self.pos + n > self.buf.numel():          # (not expected: sized from the stage widths)
+            return torch.zeros((self.N, C, 2), device=self.buf.device, dtype=torch.float64)
+        t = self.buf[self.pos:self.pos + n].view(self.N, C, 2)
+        self.pos += n
+        return t
+
+
 class GeneratorEngine:
     def __init__(self, channels):
         c = self.c = channels
@@ -118,14 +135,16 @@ class GeneratorEngine:
         return b.contiguous()
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _stage_fwd(self, P, s, a_in, dtype, keep=True):
+    def _stage_fwd(self, P, s, a_in, dtype, keep=True, arena=None):
         """keep=False (inference): intermediates are dropped as soon as their consumer has been
         launched, so the caching allocator recycles them within the stage."""
         g = self.geom
         C = self.width[s]
         N = a_in.shape[0]
         dev = a_in.device
-        st0 = ops.new_stats(N, C, dev)
+        if arena is None:
+            arena = _StatsArena(N, 3 * C, dev)
+        st0 = arena.take(C)
         if (self.convT_slab and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
                 C % 16 == 0 and C * self.inwidth[s] <= 64 * 128 and a_in.shape[2] % 8 == 0):
             # (weights of a phase resident in shared memory: 128 -> 64 measured 0.64 -> 0.49 ms per 16 images at 256^2;
@@ -154,7 +173,7 @@ class GeneratorEngine:
         if not keep:
             del att
         b = torch.empty_like(a1)
-        stb = ops.new_stats(N, C, dev)
+        stb = arena.take(C)
         if self.use_slab and dtype == torch.bfloat16 and C in self._msb_prog and a1.shape[2] % 8 == 0:
             # one launch for the 1x1 + 3x3 dil 1/2/4 branches: they share each input-row slab
             wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
@@ -172,7 +191,7 @@ class GeneratorEngine:
             for i in range(1, 5):
                 n = f"{s}.4.branch{i}.0"
                 g[n].forward(a1, self._packed(P, n, "fwd", dtype), self._bias(P, n), out=b, co_off=(i - 1) * (C // 4), stats=stb)
-        stf = ops.new_stats(N, C, dev)
+        stf = arena.take(C)
         n = f"{s}.4.fusion.0"
         wf = self._packed(P, n, "fwd", dtype)
         if not keep and self.fuse_in_norm and g[n].fused_in_norm_ok(b, wf):
@@ -197,7 +216,8 @@ class GeneratorEngine:
             # sizes raise there too.
             raise RuntimeError(f"EnhancedGenerator: H and W must be multiples of 16, got {H}x{W}")
         x0 = ops.nchw_to_nhwc(x, dtype, self.edge_pad(dtype))
-        sti = ops.new_stats(N, self.c, x.device)
+        arena = _StatsArena(N, self.c + 3 * (self.width["down1"] + self.width["down2"]), x.device)
+        sti = arena.take(self.c)
         if self.use_slab and dtype == torch.bfloat16 and self._in_prog is not None and W % 8 == 0:
             prog = self._in_prog
             wsl = self._slab_cached(P, ("initial", "slab_w"), ["initial.0.weight"],
@@ -209,7 +229,7 @@ class GeneratorEngine:
         saved = {"x0": x0, "yi": yi, "sti": sti} if save else None
         for s in ("down1", "down2"):
             a_in = a
-            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"))
+            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"), arena=arena)
             if save:
                 saved[s] = sv if save == "full" else {"a_in": a_in}
         return a, saved
@@ -217,9 +237,10 @@ class GeneratorEngine:
     def decode(self, P, a, dtype, save):
         """a: [N,H/4,W/4,4c] NHWC -> (y fp32 NCHW in [-1,1], saved)."""
         saved = {} if save else None
+        arena = _StatsArena(a.shape[0], 3 * (self.width["up1"] + self.width["up2"]), a.device)
         for s in ("up1", "up2"):
             a_in = a
-            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"))
+            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"), arena=arena)
             if save:
                 saved[s] = sv if save == "full" else {"a_in": a_in}
         N, H, W, _ = a.shape

@@ -95,7 +95,7 @@ def test_tc_nchw_tanh_epilogue_and_accumulate():
 
 
 # ---- row-slab kernel (csrc/conv_slab.cu) ---------------------------------------------------------
-@pytest.mark.parametrize("C,H,W", [(64, 16, 128), (64, 8, 256), (128, 8, 128), (64, 12, 72), (256, 4, 128)])
+@pytest.mark.parametrize("C,H,W", [(64, 16, 128), (64, 8, 256), (128, 8, 128), (64, 12, 72), (256, 4, 128), (128, 7, 72), (128, 6, 200)])
 def test_slab_msb_branches(C, H, W):
     """fused 1x1 + 3x3 dil 1/2/4 branches == the four separate convs + cat, incl. shared IN statistics"""
     from multi_style_transfer_gan_b200 import ops, slab
