@@ -142,7 +142,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-CONV_DRAM_BYTES_PER_LAUNCH = 552.87e6   # profiles/r1_launch_list_summary.md (final code of round 1)
+CONV_DRAM_BYTES_PER_LAUNCH = 675.61e6   # profiles/r1_launch_list_summary.md (final code of round 1)
 
 
 def run_ours(args):
@@ -240,7 +240,7 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "kernel": "conv_tma_kernel + conv_slab_kernel + conv_shift_kernel (every conv / convT launch of the step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"],
-                                # dram__bytes_read.sum + dram__bytes_write.sum per conv launch (average over the 128 conv launches
+                                # dram__bytes_read.sum + dram__bytes_write.sum per conv launch (average over the 138 conv launches
                                 # of the ncu window in profiles/r1_launches_final.csv, 16-image micro-batch at 512^2)
                                 "traffic": CONV_DRAM_BYTES_PER_LAUNCH if (H == 512 and args.micro_batch == 16 and c == 64) else None,
                                 "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",
