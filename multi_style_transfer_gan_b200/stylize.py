@@ -92,8 +92,16 @@ class MultiStyleStylizer:
             torch.cuda.current_stream(self.device).synchronize()
             gr = torch.cuda.CUDAGraph()
             l0 = _lib.launches
-            with torch.cuda.graph(gr):
-                self._forward_chunk(sx, weights, w_x, gain, clip, sd)
+            try:
+                with torch.cuda.graph(gr):
+                    self._forward_chunk(sx, weights, w_x, gain, clip, sd)
+            except Exception as e:                # capture refused (e.g. a user-supplied transformer block that syncs):
+                import warnings                   # same kernels, launched one by one
+                warnings.warn(f"MultiStyleStylizer: CUDA-graph capture failed ({e!r}); continuing without graphs")
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                self._forward_chunk(xi, weights, w_x, gain, clip, dst)
+                return
             while len(self._graphs) >= 8:         # stale keys (old parameter versions, other shapes): drop the oldest
                 self._graphs.pop(next(iter(self._graphs)))
             ent = self._graphs[key] = (gr, sx, sd, _lib.launches - l0)
