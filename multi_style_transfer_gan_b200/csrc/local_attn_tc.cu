@@ -24,9 +24,12 @@ using namespace la;
 constexpr int LT_THREADS = 128;
 constexpr int LT_WARPS = 4;
 constexpr int P16 = 16;
+#ifndef LA_CTAS_128
+#define LA_CTAS_128 4   // 5 (96 registers, no spills) measured the same 0.40 ms: not occupancy-bound
+#endif
 
 template <int C, bool POLY>
-__global__ void __launch_bounds__(LT_THREADS, (C == 64 ? 8 : C == 128 ? 4 : 3))
+__global__ void __launch_bounds__(LT_THREADS, (C == 64 ? 8 : C == 128 ? LA_CTAS_128 : 3))
 local_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int H, int W,
                          __nv_bfloat16* __restrict__ out) {
   constexpr int PITCH = 2 * C + 16;           // bytes per pixel row of one of q / k / v
@@ -215,7 +218,7 @@ int launch_impl(const __nv_bfloat16* qkv, int N, int H, int W, __nv_bfloat16* ou
   MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "local_attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const long long nwin = (long long)N * (H / 4) * (W / 4);
   MSG_REQUIRE(nwin + 64LL * 1024 < 0x7fffffffLL, MSG_ERR_SHAPE, "local_attn_tc: too many windows");
-  const int per_sm = C >= 256 ? 3 : (C >= 128 ? 4 : 8);   // resident CTAs per SM (smem / register limits)
+  const int per_sm = C >= 256 ? 3 : (C >= 128 ? LA_CTAS_128 : 8);   // resident CTAs per SM (smem / register limits)
   long long grid = (long long)per_sm * sm_count();
   if (grid > nwin) grid = nwin;
   local_attn_fwd_tc_kernel<C, POLY><<<(unsigned)grid, LT_THREADS, smem, st>>>(qkv, N, H, W, out);
