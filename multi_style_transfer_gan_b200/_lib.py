@@ -135,10 +135,17 @@ def check(rc):
 
 
 def require_device(index):
-    """Raises unless the *current* CUDA device is sm_100 (checked once per device)."""
+    """Raises unless CUDA device `index` (the device that owns the tensors of the call) is sm_100; checked once per
+    device.  msg_check_device() answers for the CURRENT device, so it is only consulted when that is `index`."""
     if index in _device_ok:
         return
-    check(load().msg_check_device())
+    lib = load()
+    import torch
+    major, minor = torch.cuda.get_device_capability(index)
+    if major != 10:
+        raise MsgError(f"msg_b200 kernels are built for sm_100a only; cuda:{index} is sm_{major}{minor} (no fallback)")
+    if torch.cuda.current_device() == index:
+        check(lib.msg_check_device())
     _device_ok.add(index)
 
 

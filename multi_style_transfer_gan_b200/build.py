@@ -18,8 +18,6 @@ SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tma.cu", "conv_slab.cu"
            "elementwise.cu", "gram.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas", "-v"]
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 

@@ -110,4 +110,16 @@ __device__ __forceinline__ void finalize_stats(double s, double ss, double inv_h
 
 int sm_count();
 
+// once-per-device latch for cudaFuncSetAttribute (a function attribute belongs to the current device's context, so a
+// process-wide flag would leave the second GPU of a multi-device process without its shared-memory opt-in)
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  int dev = 0;
+  bool needed() {
+    cudaGetDevice(&dev);
+    return !((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull);
+  }
+  void done() { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+
 }  // namespace msg

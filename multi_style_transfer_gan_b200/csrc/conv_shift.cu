@@ -380,11 +380,11 @@ extern "C" int msg_conv_shift(const msg_shift_desc* d, const void* x, const void
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_shift: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;     // cudaFuncSetAttribute is per device
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_shift: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
   int grid = sm_count();
   const long long total = (long long)d->N * d->H * p.segs;

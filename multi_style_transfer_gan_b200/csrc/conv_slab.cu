@@ -792,8 +792,8 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_slab: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;     // cudaFuncSetAttribute is per device
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -801,7 +801,7 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_slab_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
   int grid = sm_count();
   const long long total = (long long)d->N * (d->H / p.trows) * p.segs;

@@ -315,11 +315,11 @@ int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float*
   p.nkb = (p.K + TC_BK - 1) / TC_BK;
   p.M = (long long)d->N * d->Hg * d->Wg;
   const size_t smem = tc_smem_bytes(p.BN);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;     // cudaFuncSetAttribute is per device
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
   dim3 grid((unsigned)((p.M + TC_BM - 1) / TC_BM), (unsigned)((d->Cout + p.BN - 1) / p.BN));
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);

@@ -611,12 +611,12 @@ int conv2d_tma(const msg_conv_desc* d, const void* x, const void* w, const float
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "conv_tma: cuTensorMapEncodeTiled(C) failed with %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;     // cudaFuncSetAttribute is per device
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "conv_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
   int grid = sm_count();
   const int total = p.m_tiles * p.n_tiles;

@@ -275,11 +275,11 @@ int conv2d_wgrad_tc_impl(const msg_conv_desc* d, const void* x, const void* dy, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;     // cudaFuncSetAttribute is per device
+  if (attr_set.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
   const int grid = p.co_tiles * p.groups * p.splits;
   conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapX, mapDY, p);

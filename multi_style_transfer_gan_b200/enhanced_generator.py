@@ -158,10 +158,10 @@ class _GeneratorFn(torch.autograd.Function):
     """Whole-generator op: one autograd node, manual backward over saved NHWC activations."""
 
     @staticmethod
-    def forward(ctx, model, dtype, keys, x, *params):
+    def forward(ctx, model, dtype, keys, grad_on, x, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
+        need = grad_on and (ctx.needs_input_grad[4] or any(ctx.needs_input_grad[5:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         a, s_enc = eng.encode(P, x, dtype, save)
         y, s_dec = eng.decode(P, a, dtype, save)
@@ -178,18 +178,18 @@ class _GeneratorFn(torch.autograd.Function):
         G = {}
         dy = dy.contiguous().float()
         da = eng.decode_bwd(P, G, s_dec, dy, dtype)
-        dx = eng.encode_bwd(P, G, s_enc, da, dtype, need_dx=ctx.needs_input_grad[3])
+        dx = eng.encode_bwd(P, G, s_enc, da, dtype, need_dx=ctx.needs_input_grad[4])
         ctx.saved = None
-        grads = tuple(G.get(k) if ctx.needs_input_grad[4 + i] else None for i, k in enumerate(keys))
-        return (None, None, None, dx) + grads
+        grads = tuple(G.get(k) if ctx.needs_input_grad[5 + i] else None for i, k in enumerate(keys))
+        return (None, None, None, None, dx) + grads
 
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, dtype, keys, x, *params):
+    def forward(ctx, model, dtype, keys, grad_on, x, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
+        need = grad_on and (ctx.needs_input_grad[4] or any(ctx.needs_input_grad[5:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         a, s_enc = eng.encode(P, x, dtype, save)
         if need:
@@ -202,17 +202,17 @@ class _EncoderFn(torch.autograd.Function):
         eng, dtype, keys = ctx.model._engine, ctx.dtype, ctx.keys
         P = dict(zip(keys, ctx.saved_tensors))
         G = {}
-        dx = eng.encode_bwd(P, G, ctx.saved, da.contiguous().to(dtype), dtype, need_dx=ctx.needs_input_grad[3])
+        dx = eng.encode_bwd(P, G, ctx.saved, da.contiguous().to(dtype), dtype, need_dx=ctx.needs_input_grad[4])
         ctx.saved = None
-        return (None, None, None, dx) + tuple(G.get(k) for k in keys)
+        return (None, None, None, None, dx) + tuple(G.get(k) for k in keys)
 
 
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, dtype, keys, a, *params):
+    def forward(ctx, model, dtype, keys, grad_on, a, *params):
         eng = model._engine
         P = dict(zip(keys, params))
-        need = model._grad_on and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:]))   # needs_input_grad ignores no_grad
+        need = grad_on and (ctx.needs_input_grad[4] or any(ctx.needs_input_grad[5:]))   # needs_input_grad ignores no_grad
         save = ("ckpt" if model._checkpointing else "full") if need else False
         y, s_dec = eng.decode(P, a.contiguous().to(dtype), dtype, save)
         if need:
@@ -227,7 +227,7 @@ class _DecoderFn(torch.autograd.Function):
         G = {}
         da = eng.decode_bwd(P, G, ctx.saved, dy.contiguous().float(), dtype)
         ctx.saved = None
-        return (None, None, None, da.float()) + tuple(G.get(k) for k in keys)
+        return (None, None, None, None, da.float()) + tuple(G.get(k) for k in keys)
 
 
 class EnhancedGenerator(nn.Module):
@@ -304,17 +304,19 @@ class EnhancedGenerator(nn.Module):
         xin = x if x.dtype == torch.float32 else x.float()
         # autograd.Function.forward always runs with grad mode off and ctx.needs_input_grad ignores no_grad, so the
         # caller's grad mode is recorded here: under no_grad nothing is saved and the inference schedule is used
-        self._grad_on = torch.is_grad_enabled()
-        if self._blocks_are_identity():
-            # style_encoder output is only consumed by the (identity) blocks: dead, skipped
-            return _GeneratorFn.apply(self, dtype, keys, xin.contiguous(), *params)
-        a = _EncoderFn.apply(self, dtype, keys, xin.contiguous(), *params)     # [B,h,w,4c]
-        B, h, w, C = a.shape
-        style = self.style_encoder[3](self.style_encoder[2](a.mean(dim=(1, 2))))  # :142-147, :216
-        t = a.reshape(B, h * w, C)                                                # :218-219
-        for block in self.transformer_blocks:
-            t = block(t, style, x)                                                # :222-223
-        return _DecoderFn.apply(self, dtype, keys, t.reshape(B, h, w, C), *params)
+        # (passed as an argument, not stored on the module: forward stays re-entrant across threads, gan_login_gui.py:755-767)
+        grad_on = torch.is_grad_enabled()
+        with torch.cuda.device(x.device):      # kernels launch on the tensors' device, whatever the caller's current device is
+            if self._blocks_are_identity():
+                # style_encoder output is only consumed by the (identity) blocks: dead, skipped
+                return _GeneratorFn.apply(self, dtype, keys, grad_on, xin.contiguous(), *params)
+            a = _EncoderFn.apply(self, dtype, keys, grad_on, xin.contiguous(), *params)     # [B,h,w,4c]
+            B, h, w, C = a.shape
+            style = self.style_encoder[3](self.style_encoder[2](a.mean(dim=(1, 2))))  # :142-147, :216
+            t = a.reshape(B, h * w, C)                                                # :218-219
+            for block in self.transformer_blocks:
+                t = block(t, style, x)                                                # :222-223
+            return _DecoderFn.apply(self, dtype, keys, grad_on, t.reshape(B, h, w, C), *params)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -354,12 +356,12 @@ class SpectralNormConv2d(_NoForward):
 
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, dtype, training, keys, x, *params):
+    def forward(ctx, model, dtype, training, keys, grad_on, x, *params):
         eng = model._engine
         P = dict(zip(keys, params))
         P.update(model._buffers_dict())
-        need_dx = model._grad_on and ctx.needs_input_grad[4]
-        need_dw = model._grad_on and any(ctx.needs_input_grad[5:])
+        need_dx = grad_on and ctx.needs_input_grad[5]
+        need_dw = grad_on and any(ctx.needs_input_grad[6:])
         save = need_dx or need_dw
         ctx.set_materialize_grads(False)   # unused head (score or struct) -> None, not zeros
         score, struct, saved = eng.forward(P, x, dtype, training, save)
@@ -377,8 +379,8 @@ class _DiscriminatorFn(torch.autograd.Function):
         dx, G = eng.backward(P, ctx.saved, None if dscore is None else dscore.contiguous(),
                              None if dstruct is None else dstruct.contiguous(), dtype, need_dx, need_dw)
         ctx.saved = None
-        grads = tuple(G.get(k) if ctx.needs_input_grad[5 + i] else None for i, k in enumerate(keys))
-        return (None, None, None, None, dx) + grads
+        grads = tuple(G.get(k) if ctx.needs_input_grad[6 + i] else None for i, k in enumerate(keys))
+        return (None, None, None, None, None, dx) + grads
 
 
 class EnhancedDiscriminator(nn.Module):
@@ -417,6 +419,7 @@ class EnhancedDiscriminator(nn.Module):
         dtype = _resolve_dtype(self.precision)
         keys, params = zip(*self.named_parameters())
         xin = x if x.dtype == torch.float32 else x.float()
-        self._grad_on = torch.is_grad_enabled()    # see EnhancedGenerator.forward
-        score, struct = _DiscriminatorFn.apply(self, dtype, self.training, tuple(keys), xin.contiguous(), *params)
+        grad_on = torch.is_grad_enabled()    # see EnhancedGenerator.forward
+        with torch.cuda.device(x.device):
+            score, struct = _DiscriminatorFn.apply(self, dtype, self.training, tuple(keys), grad_on, xin.contiguous(), *params)
         return score.squeeze(), struct      # .squeeze(): 0-dim when B == 1 (:275)

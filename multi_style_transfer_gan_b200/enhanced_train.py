@@ -58,6 +58,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.grad = self.flat_grad[off:off + k].view_as(p)
             off += k
         self.step_count = 0
+        self._params = params
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()   # keep the views alive: autograd accumulates into them in place
@@ -68,6 +69,13 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
                       g["betas"][1], g["eps"], self.step_count, grad_scale)
+        self.bump_versions()
+
+    def bump_versions(self):
+        """The kernel wrote through raw pointers: bump the version counter of every parameter (a Parameter whose .data was
+        re-pointed keeps its own counter, separate from the flat buffer's) so packed-weight caches and captured graphs
+        keyed on (data_ptr, _version) see the update without an explicit invalidate call."""
+        torch.autograd.graph.increment_version([self.flat] + self._params)
 
 
 class EnhancedCycleGAN:
@@ -99,8 +107,24 @@ class EnhancedCycleGAN:
         dp = [p for m in (self.D_A, self.D_B) for p in m.parameters()]
         self.g_optimizer = FusedAdam(gp, lr=5e-5, betas=(0.5, 0.999))
         self.d_optimizer = FusedAdam(dp, lr=2e-4, betas=(0.5, 0.999))
+        self._broadcast_replica_state()
         for m in (self.G_AB, self.G_BA):
             m.invalidate_packed_weights()
+
+    def _broadcast_replica_state(self):
+        """Data parallel: every rank must start from rank 0's parameters, Adam state and spectral-norm u / v buffers
+        (randomly initialised, enhanced_generator.py:269-271) -- otherwise the replicas silently train different models
+        (the gradient all-reduce alone does not keep them together)."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        with torch.cuda.device(self.device):
+            for opt in (self.g_optimizer, self.d_optimizer):
+                for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq):
+                    dist.broadcast(t, src=0)
+                opt.bump_versions()
+            for m in (self.D_A, self.D_B):
+                for b in m.buffers():
+                    dist.broadcast(b, src=0)
 
     def set_precision(self, precision):
         self.precision = precision
@@ -121,6 +145,10 @@ class EnhancedCycleGAN:
     def train_step(self, real_A, real_B):
         """reference: enhanced_train.py:59-131 (order of the 6 G and 10 D forwards preserved, so the
         spectral-norm power iterations advance exactly as in the reference)."""
+        with torch.cuda.device(self.device):
+            return self._train_step(real_A, real_B)
+
+    def _train_step(self, real_A, real_B):
         G_AB, G_BA, D_A, D_B = self.G_AB, self.G_BA, self.D_A, self.D_B
         real_A = real_A.to(self.device, non_blocking=True)
         real_B = real_B.to(self.device, non_blocking=True)

@@ -31,7 +31,10 @@ _raw_device = getattr(torch._C, "_cuda_getDevice", None)
 
 def _stream():
     """Raw handle of torch's current stream on the current device.  torch.cuda.current_stream() builds a Python Stream
-    object (~15 us, a quarter of the host time of a launch-bound train step); the raw accessor costs ~0.3 us."""
+    object (~15 us, a quarter of the host time of a launch-bound train step); the raw accessor costs ~0.3 us.
+    The C-ABI launches on the CURRENT device (it never calls cudaSetDevice): `_dev` below refuses tensors that live on
+    another device, and the module-level entry points (EnhancedGenerator.forward, ...) run under
+    ``torch.cuda.device(x.device)``."""
     if _raw_stream is not None and _raw_device is not None:
         return ctypes.c_void_p(_raw_stream(_raw_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -40,7 +43,13 @@ def _stream():
 def _dev(t):
     if not t.is_cuda:
         raise _lib.MsgError("msg_b200 ops need CUDA tensors: there is no CPU fallback in this package")
-    _lib.require_device(t.device.index)
+    idx = t.device.index
+    cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+    if idx != cur:
+        # a launch on the current device with another device's pointers = illegal address at best, silent peer traffic at worst
+        raise _lib.MsgError(f"msg_b200 op on a cuda:{idx} tensor while the current device is cuda:{cur}: the kernels launch "
+                            f"on the current device -- wrap the call in `with torch.cuda.device({idx}):`")
+    _lib.require_device(idx)
 
 
 def conv_raw(desc, x, w, bias, y, stats=None, in_stats=None):

@@ -158,9 +158,9 @@ class _Engine:
 
 class _PretrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, dtype, training, keys, x, *params):
+    def forward(ctx, model, dtype, training, keys, grad_on, x, *params):
         P = dict(zip(keys, params))
-        need = model._grad_on and (ctx.needs_input_grad[4] or any(ctx.needs_input_grad[5:]))
+        need = grad_on and (ctx.needs_input_grad[5] or any(ctx.needs_input_grad[6:]))
         if need and not training:
             raise NotImplementedError("pretrain.Generator (msg_b200): backward is implemented for train() mode "
                                       "(batch statistics); use no_grad for eval-mode inference")
@@ -173,10 +173,10 @@ class _PretrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         P = dict(zip(ctx.keys, ctx.saved_tensors))
-        G, dx = ctx.model._engine.backward(P, ctx.tape, ctx.y_full, dy, ctx.dtype, ctx.needs_input_grad[4])
+        G, dx = ctx.model._engine.backward(P, ctx.tape, ctx.y_full, dy, ctx.dtype, ctx.needs_input_grad[5])
         ctx.tape = ctx.y_full = None
-        grads = tuple(G.get(k) if ctx.needs_input_grad[5 + i] else None for i, k in enumerate(ctx.keys))
-        return (None, None, None, None, dx) + grads
+        grads = tuple(G.get(k) if ctx.needs_input_grad[6 + i] else None for i, k in enumerate(ctx.keys))
+        return (None, None, None, None, None, dx) + grads
 
 
 class Generator(nn.Module):
@@ -198,7 +198,6 @@ class Generator(nn.Module):
         self.channels = c
         self._engine = _Engine(c)
         self.precision = "fp32"
-        self._grad_on = True
 
     def set_precision(self, precision):
         if precision not in ("fp32", "bf16"):
@@ -216,8 +215,54 @@ class Generator(nn.Module):
             raise RuntimeError("pretrain.Generator (msg_b200): a CUDA tensor is required; there is no CPU path")
         dtype = torch.bfloat16 if (self.precision == "bf16" or torch.is_autocast_enabled()) else torch.float32
         keys, params = zip(*self.named_parameters())
-        self._grad_on = torch.is_grad_enabled()
-        return _PretrainFn.apply(self, dtype, self.training, tuple(keys), x.float().contiguous(), *params)
+        grad_on = torch.is_grad_enabled()      # an argument, not module state: forward stays re-entrant
+        with torch.cuda.device(x.device):
+            return _PretrainFn.apply(self, dtype, self.training, tuple(keys), grad_on, x.float().contiguous(), *params)
+
+
+def set_seed(seed=42):
+    """reference: pretrain.py:13-17 (host utility kept so `from pretrain import set_seed` resolves against dropin/)."""
+    import random
+
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+class MonetPhotoDataset(torch.utils.data.Dataset):
+    """reference: pretrain.py:20-57 -- `<root>/<split><domain>/*.jpg|*.png`, resize + centre crop to img_size,
+    Normalize(0.5, 0.5), and an 8 x 8 grid mask hiding each cell with probability 0.4; returns
+    (masked_image, image, mask).  Host-side data loading only (not on the hot path); kept so that
+    the reference's `from pretrain import MonetPhotoDataset` (enhanced_train.py:11, m_test.py:12) works with dropin/."""
+
+    def __init__(self, root_dir, domain, split="train", img_size=256):
+        from pathlib import Path
+
+        from torchvision import transforms
+        self.root_dir, self.domain, self.split, self.img_size = Path(root_dir), domain, split, img_size
+        folder = self.root_dir / f"{split}{domain}"
+        self.image_paths = list(folder.glob("*.jpg")) + list(folder.glob("*.png"))
+        self.transform = transforms.Compose([
+            transforms.Resize(img_size), transforms.CenterCrop(img_size), transforms.ToTensor(),
+            transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def __getitem__(self, idx):
+        import random
+
+        from PIL import Image
+        image = self.transform(Image.open(self.image_paths[idx]).convert("RGB"))
+        mask = torch.ones_like(image)
+        cell = self.img_size // 8
+        for i in range(8):                 # same draw order as the reference: row-major cells, one random() each
+            for j in range(8):
+                if random.random() < 0.4:
+                    mask[:, i * cell:(i + 1) * cell, j * cell:(j + 1) * cell] = 0
+        return image * mask, image, mask
 
 
 def pretrain_step(generator, optimizer, masked_imgs, real_imgs, masks, max_norm=1.0):

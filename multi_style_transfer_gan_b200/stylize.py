@@ -104,8 +104,11 @@ class MultiStyleStylizer:
                 return
             while len(self._graphs) >= 8:         # stale keys (old parameter versions, other shapes): drop the oldest
                 self._graphs.pop(next(iter(self._graphs)))
-            ent = self._graphs[key] = (gr, sx, sd, _lib.launches - l0)
-        gr, sx, sd, n_launches = ent
+            # the captured launches address the packed weights of each generator's cache (allocated during the warm-up, outside
+            # the graph's pool): the entry keeps them alive, so invalidate_packed_weights() cannot free memory a graph reads
+            keep = [list(g._engine._cache.values()) for g in self.generators]
+            ent = self._graphs[key] = (gr, sx, sd, _lib.launches - l0, keep)
+        gr, sx, sd, n_launches = ent[:4]
         sx.copy_(xi)
         gr.replay()
         _lib.launches += n_launches               # kernels inside the replayed graph (the launch counter is per C-ABI call)
@@ -123,6 +126,10 @@ class MultiStyleStylizer:
         S = len(self.generators)
         if len(weights) != S:
             raise ValueError(f"{S} styles but {len(weights)} weights")
+        with torch.cuda.device(self.device):
+            return self._run(x, weights, w_x, gain, clip, out_uint8, out)
+
+    def _run(self, x, weights, w_x, gain, clip, out_uint8, out):
         B = x.shape[0]
         mb = self.micro_batch
         host_in = not x.is_cuda
@@ -165,4 +172,10 @@ class MultiStyleStylizer:
                 self._forward_chunk(xi, weights, w_x, gain, clip, dst)
             if host_out:
                 out[lo:hi].copy_(dst, non_blocking=True)
+        if host_out:
+            # the D2H copies into a (pinned) host tensor are asynchronous: the caller is about to read / save the images,
+            # so the call returns only when the last copy has landed (one event wait, not a device-wide synchronize)
+            done = torch.cuda.Event()
+            done.record(cur)
+            done.synchronize()
         return out

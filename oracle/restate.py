@@ -3,7 +3,7 @@
 This is the oracle the CUDA path is checked against.  It is a *functional* restatement that
 works directly on ``state_dict`` tensors (no nn.Module tree), so it travels to the GPU box where
 /root/reference does not exist.  It is pinned against the real reference by
-``tests/test_oracle_vs_reference.py`` (container only) and against the committed golden vectors
+``tests/test_init_matches_reference.py`` (container only) and against the committed golden vectors
 in ``tests/golden/`` (everywhere); the goldens were produced by ``oracle/make_golden.py`` from
 the unmodified reference.
 
@@ -13,8 +13,12 @@ reference`` legs may import this module.  The product package never does.
 Parity status
   * generator / discriminator / train_step / blends: PINNED (reference imported, goldens).
   * StructuralTransformerBlock: source missing from the reference -> identity, parity UNPINNED.
-  * blended-affine InstanceNorm, Gram/VGG style loss: not in the reference
-    -> restated from the published formulation (Gatys et al. / Johnson et al.), parity UNPINNED.
+  * blended-affine InstanceNorm: not in the reference -> parity UNPINNED (with gamma = 1, beta = 0 it
+    reduces to the pinned InstanceNorm).
+  * Gram/VGG style loss: not in the reference.  The VGG-19 trunk restatement is PINNED against the named
+    dependency -- torchvision 0.26 ``vgg19(weights=None).features[:30]`` taps on shared seeded weights
+    (tests/test_oracle_vgg_torchvision.py); the Gram / loss normalisation follows the published formulation
+    (Gatys et al. / Johnson et al.: G = F F^T / (C H W), mean squared difference per layer) and has no reference to pin.
 
 Every function cites the reference lines it follows (relative to /root/reference).
 """
