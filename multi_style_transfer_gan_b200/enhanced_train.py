@@ -140,7 +140,17 @@ class EnhancedCycleGAN:
             m.invalidate_packed_weights()
 
     def _sync_grads(self, opt):
-        return allreduce_flat_(opt.flat_grad)
+        """One NCCL sum all-reduce over the optimizer's flat gradient buffer.  With ``self.comm_log`` set to a list, the call is
+        bracketed by CUDA events on the launching stream (bench.py reports the time spent in the collective)."""
+        log = getattr(self, "comm_log", None)
+        if log is None or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return allreduce_flat_(opt.flat_grad)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scale = allreduce_flat_(opt.flat_grad)
+        e1.record()
+        log.append((e0, e1, opt.flat_grad.numel() * 4))
+        return scale
 
     def train_step(self, real_A, real_B):
         """reference: enhanced_train.py:59-131 (order of the 6 G and 10 D forwards preserved, so the
