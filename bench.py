@@ -255,10 +255,10 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
     H = W = args.size
     scale = (H * W) / 512 ** 2
     out = {}
-    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_la_stage")
+    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_la_stage_fwd")
     conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in conv_keys) / args.steps
     conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in conv_keys) // args.steps
-    fused_la = breakdown.get("msg_la_stage", {}).get("launches", 0) > 0
+    fused_la = breakdown.get("msg_la_stage_fwd", {}).get("launches", 0) > 0
     # algorithmic flops of those launches: conv + convT always; the LocalAttention bmm flops ride in the fused stage kernel
     # (when every stage is fused) -- the stand-alone attention core launches (msg_local_attn_fwd) are not in this family
     la_all_fused = fused_la and breakdown.get("msg_local_attn_fwd", {}).get("launches", 0) == 0

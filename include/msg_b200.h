@@ -230,6 +230,29 @@ int msg_local_attn_bwd(int dtype, const void* qkv, const void* dout, int N, int 
                        int ws, void* dqkv, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused LocalAttention STAGE (the whole of LocalAttention.forward, enhanced_generator.py:13-47, window_size 4)
+ * as ONE tcgen05 kernel: [optional InstanceNorm + ReLU of the producer, from its raw plane sums] -> qkv 1x1 conv
+ * -> window attention (logits and probabilities never leave the SM: S in TMEM, P written back to TMEM and fed
+ * to the P.V MMA from there) -> proj 1x1 conv.  Replaces msg_conv2d(qkv) + msg_local_attn_fwd + msg_conv2d(proj)
+ * on the inference path; HBM traffic = x in + out.
+ *   x      [N,H,W,C]  bf16 NHWC (raw conv output when in_stats != NULL, else the already normalised input)
+ *   in_stats  fp64 [N][C][2] raw plane sums of x (msg_conv2d's MSG_CONV_STATS output) or NULL; in_act: MSG_ACT_NONE/RELU
+ *   wqkv   [3C][C] bf16 (msg_pack_conv_weight MSG_PACK_FWD of qkv.weight), bqkv fp32 [3C]
+ *   wproj  [C][C]  bf16 (same packing of proj.weight), bproj fp32 [C]
+ *   out    [N,H,W,C]  bf16
+ * Supported: bf16, C in {64, 128}, H % 4 == 0, W % 4 == 0, 16-byte aligned pointers (msg_la_stage_supported
+ * returns 1); anything else: the three separate calls above.
+ * ------------------------------------------------------------------------------------------- */
+int msg_la_stage_supported(int dtype, int N, int H, int W, int C, const void* x, const void* wqkv,
+                           const void* wproj, const void* out);
+/* development hook, effective only in builds with -DMSG_LA_TRACE: device buffer (19 x 4096 u64) that receives the
+ * role timelines of CTA 0 (tools/la_trace.py); NULL switches it off. */
+int msg_la_stage_set_trace(void* buf);
+int msg_la_stage_fwd(int dtype, const void* x, const double* in_stats, int in_act, const void* wqkv,
+                     const float* bqkv, const void* wproj, const float* bproj, int N, int H, int W, int C,
+                     void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * layout / image helpers
  * ------------------------------------------------------------------------------------------- */
 /* fp32 NCHW [N,C,H,W] -> NHWC dtype [N,H,W,Cp] (channels >= C zero-filled)  and back. */

@@ -75,6 +75,9 @@ SIGNATURES = {
     "msg_instnorm_bwd": [c_int, _P, _P, _P, c_int, c_ll, c_int, c_int, _P, _P, _P],
     "msg_local_attn_fwd": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "msg_local_attn_bwd": [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "msg_la_stage_set_trace": [_P],
+    "msg_la_stage_supported": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "msg_la_stage_fwd": [c_int, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "msg_nchw_to_nhwc": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "msg_nhwc_to_nchw": [c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "msg_blend_outputs": [ctypes.POINTER(_P), ctypes.POINTER(c_float), c_int, _P, c_float, c_float,

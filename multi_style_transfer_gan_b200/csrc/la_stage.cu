@@ -1,0 +1,702 @@
+// Fused LocalAttention stage (enhanced_generator.py:13-47), ONE tcgen05 kernel per stage (sm_100a, bf16):
+//
+//     [InstanceNorm + ReLU of the producing conv, applied to the landed tile]  ->  qkv 1x1 conv  ->  per 4x4 window:
+//     S = normalize(q) normalize(k)^T  [C x C]  ->  softmax over the last dim  ->  P v  ->  proj 1x1 conv
+//
+// The reference materialises qkv ([.., 3C]), the window-permuted copies, the logits ([nW, C, C], larger than the
+// activation), the attention output and the projected output in global memory; round 1 ran three launches with a 3C
+// channel HBM round trip.  Here the only HBM traffic is the C-channel input tile and the C-channel output tile.
+//
+// Tile = 128 pixels = 8 windows (4 rows x 32 columns of one image), brought in by a 5-D TMA box ordered
+// (channel, x-in-window, y-in-window, window column) so that tile row r = 16 * window + pixel-in-window.
+//
+//   warp 0      TMA producer: x tiles; at C=128 also the streamed weight K blocks (C=64: weights resident in smem)
+//   warp 1      issuer G: the 1x1-conv GEMMs on tcgen05 -- qkv as three N=C chunks (q | k | v) of M=128 pixels into a
+//               two-slot TMEM accumulator ring, and the projection of the PREVIOUS tile (A operand = attention output,
+//               MN-major in smem)
+//   warp 2      issuer A: per window (C=128) / window pair (C=64, block-diagonal) S = Qh^T Kh as ONE tcgen05.mma with both
+//               operands MN-major (K = the 16 pixels), then P.V with the A operand read FROM TENSOR MEMORY (P is written
+//               back over S by the softmax warps, FA4 style) and V (+ a group of all-ones rows that yields the softmax row
+//               sums in fp32 for free) K-major from smem; S/P/O double-buffered in TMEM
+//   warps 4-7   drain: tcgen05.ld of the q / k / v accumulators (thread = pixel: the L2 norm over channels is
+//               thread-local), + bias, normalise, -> bf16 (q, k, k pre-multiplied by log2 e) / fp16 (v) operand tiles
+//   warps 8-11 (+12-15)  softmax: tcgen05.ld S (thread = row i), exp2 (half MUFU, half packed fp16 polynomial on the FMA
+//               pipe; |S| <= 1 so no running max), tcgen05.st P (fp16) in place
+//   next 4      O drain + epilogue: O / rowsum -> bf16 -> the projection's A operand; then projection accumulators
+//               + bias -> bf16 -> 128B-swizzled staging -> per-warp 5-D TMA store
+//   last 4      (XF) transform warps: InstanceNorm + ReLU of the landed x tile in shared memory, exactly the arithmetic
+//               of the stand-alone apply kernel (as conv_tma.cu)
+//
+// TMEM (512 columns): [0, 2C) accumulator ring (slot 0: q, v; slot 1: k, proj), then two 128-column S buffers; inside an
+// S buffer P occupies columns [0, C/2) and O columns [C/2, C/2 + N_pv).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "la_mma.cuh"
+#include "tcgen05.cuh"
+
+namespace msg {
+namespace {
+using namespace tc;
+
+template <int C>
+struct Cfg {
+  static constexpr int KB = C / 64;                    // 64-channel blocks
+  static constexpr int UNITS = C == 64 ? 4 : 8;        // attention units per tile: window pairs (C=64) / windows (C=128)
+  static constexpr int NPV = C == 64 ? 48 : 32;        // N of the P.V MMA: [16 px | 8 ones] per window (+ 8 don't-care at C=128)
+  static constexpr int XS = C == 64 ? 2 : 1;           // x-tile stages
+  static constexpr int WS = 2;                         // streamed-weight stages (C=128)
+  static constexpr int X_TILE = 128 * 128;             // one K block of an x tile: 128 pixel rows x 128 B
+  static constexpr int X_BYTES = KB * X_TILE;
+  static constexpr int OFF_X = 0;
+  static constexpr int W_BYTES = C == 64 ? (192 + 64) * 128 : WS * 128 * 128;
+  static constexpr int OFF_W = OFF_X + XS * X_BYTES;
+  static constexpr int QK_BYTES = KB * 8 * 2048;       // [mn block][window][16 pixel rows x 128 B]
+  static constexpr int OFF_Q = OFF_W + W_BYTES;
+  static constexpr int OFF_K = OFF_Q + QK_BYTES;
+  static constexpr int V_KB = 8 * 3072;                // per K block: [window][16 pixel rows + 8 ones rows][128 B]
+  static constexpr int OFF_V = OFF_K + QK_BYTES;
+  static constexpr int V_BYTES = KB * V_KB + 1024;     // + the 4th (don't-care) row group of the last window
+  static constexpr int OFF_A = OFF_V + V_BYTES;        // attention output = A of the projection; later the store staging
+  static constexpr int A_BYTES = KB * 128 * 128;
+  static constexpr int OFF_BIAS = OFF_A + A_BYTES;     // 3C qkv biases + C proj biases (fp32)
+  static constexpr int OFF_XF = OFF_BIAS + 4 * C * 4;  // fused input norm: scale[C], shift[C]
+  static constexpr int OFF_BAR = OFF_XF + 2 * C * 4;
+  static constexpr int SMEM = OFF_BAR + 512 + 1024;    // + alignment slack
+  static constexpr int SCOL0 = 2 * C;                  // first S buffer column
+  static constexpr int OOFF = C / 2;                   // O columns inside an S buffer
+  static_assert(OFF_A % 1024 == 0 && OFF_V % 1024 == 0 && OFF_Q % 1024 == 0, "operand tiles must be 1024-byte aligned");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct LaParams {
+  int N, H, W;
+  int tiles_w, tiles_per_img, total_tiles;
+  const float* bqkv;
+  const float* bproj;
+  const double* in_stats;     // XF: raw plane sums [N][C][2] of the input tensor
+  int in_act;
+  unsigned long long* trace;  // MSG_LA_TRACE builds only: [role][event] = (tag, clock) pairs of CTA 0
+};
+
+#ifdef MSG_LA_TRACE
+// timeline instrumentation (development builds: python -m multi_style_transfer_gan_b200.build with MSG_LA_TRACE=1):
+// lane 0 of each role of CTA 0 appends (event, tile, unit, clock64) -- read back with tools/la_trace.py
+#define TR_DECL(role) unsigned long long* tr_ = (p.trace && blockIdx.x == 0 && lane == 0) ? p.trace + (role) * 4096 : nullptr; int tr_n = 0
+#define TR(ev, lt_, u_) do { if (tr_ && tr_n < 2047) { tr_[2 * tr_n] = ((unsigned long long)(ev) << 32) | ((unsigned long long)(lt_) << 8) | (unsigned long long)(u_); tr_[2 * tr_n + 1] = clock64(); ++tr_n; tr_[4094] = tr_n; } } while (0)
+#else
+#define TR_DECL(role) do {} while (0)
+#define TR(ev, lt_, u_) do {} while (0)
+#endif
+
+enum Bar {
+  B_XFULL = 0, B_XEMPTY = 2, B_XFDONE = 4, B_WFULL = 6, B_WEMPTY = 8, B_WRES = 10, B_ACCFULL = 11, B_ACCEMPTY = 13,
+  B_QKREADY = 15, B_VREADY = 16, B_OPSFREE = 17, B_SFULL = 18, B_PREADY = 20, B_OFULL = 22, B_OEMPTY = 24, B_ASREADY = 26,
+  B_PFULL = 27, B_PEMPTY = 28,      // projection accumulators (TMEM slot 1, shared with k): their own barriers, because a parity wait only
+                                    // separates ADJACENT phases and slot 1 has two consumers (drain warps: k; epilogue warps: proj)
+  B_COUNT = 29
+};
+
+__device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int C, int NSM, bool XF>
+__global__ void __launch_bounds__(32 * (12 + 4 * NSM + (XF ? 4 : 0)), 1)
+la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWqkv,
+                const __grid_constant__ CUtensorMap mapWproj, const __grid_constant__ CUtensorMap mapOut, const LaParams p) {
+  using K = Cfg<C>;
+  constexpr int KB = K::KB, UNITS = K::UNITS;
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sX = base + K::OFF_X, sW = base + K::OFF_W, sQ = base + K::OFF_Q, sK = base + K::OFF_K, sV = base + K::OFF_V,
+                 sA = base + K::OFF_A, sBar = base + K::OFF_BAR;
+  float* sbias = reinterpret_cast<float*>(gen + K::OFF_BIAS);
+  float* xf_tab = reinterpret_cast<float*>(gen + K::OFF_XF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + K::OFF_BAR + 8 * B_COUNT);
+  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+
+  // ---- one-time setup
+  for (int i = tid; i < 4 * C; i += (int)blockDim.x) sbias[i] = i < 3 * C ? p.bqkv[i] : p.bproj[i - 3 * C];
+  // the all-ones row group of every window of V (fp16 1.0): P.[ones] = softmax row sums, accumulated in fp32 by the MMA
+  for (int i = tid; i < KB * 8 * 64; i += (int)blockDim.x) {
+    const int kb = i / (8 * 64), w = (i / 64) & 7, c16 = i & 63;
+    *reinterpret_cast<uint4*>(gen + K::OFF_V + kb * K::V_KB + w * 3072 + 2048 + c16 * 16) =
+        make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar(B_XFULL + s), 1); mbar_init(bar(B_XEMPTY + s), 1); mbar_init(bar(B_XFDONE + s), 4);
+        mbar_init(bar(B_WFULL + s), 1); mbar_init(bar(B_WEMPTY + s), 1);
+        mbar_init(bar(B_ACCFULL + s), 1); mbar_init(bar(B_ACCEMPTY + s), 4);
+        mbar_init(bar(B_SFULL + s), 1); mbar_init(bar(B_PREADY + s), 4);
+        mbar_init(bar(B_OFULL + s), 1); mbar_init(bar(B_OEMPTY + s), 4);
+      }
+      mbar_init(bar(B_WRES), 1); mbar_init(bar(B_QKREADY), 4); mbar_init(bar(B_VREADY), 4); mbar_init(bar(B_OPSFREE), 1);
+      mbar_init(bar(B_ASREADY), 4); mbar_init(bar(B_PFULL), 1); mbar_init(bar(B_PEMPTY), 4);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapWqkv)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapWproj)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapOut)) : "memory");
+  }
+  fence_proxy_async();        // the generic-proxy ones rows above are read by tcgen05.mma
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // contiguous tile range of this CTA (same image, neighbouring tiles; the norm table is rebuilt per image)
+  const int t_begin = (int)((long long)blockIdx.x * p.total_tiles / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
+  const int T = t_end - t_begin;
+  auto tile_coords = [&](int t, int& img, int& h0, int& wc0) {
+    img = t / p.tiles_per_img;
+    const int rem = t - img * p.tiles_per_img;
+    const int th = rem / p.tiles_w;
+    h0 = th * 4;
+    wc0 = (rem - th * p.tiles_w) * 8;
+  };
+  const uint32_t hi = (uint32_t)(make_sw128_desc(0) >> 32);     // SBO = 1024, version, SWIZZLE_128B: shared by every descriptor here
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      if (C == 64) {
+        mbar_expect_tx(bar(B_WRES), (192 + 64) * 128);
+        tma_load_2d(sW, &mapWqkv, bar(B_WRES), 0, 0);
+        tma_load_2d(sW + 192 * 128, &mapWproj, bar(B_WRES), 0, 0);
+      }
+      TR_DECL(0);
+      int ws = 0;
+      uint32_t wn = 0;                                   // weight loads issued
+      auto wload = [&](const CUtensorMap* m, int col, int row) {
+        if (wn >= (uint32_t)K::WS) mbar_wait(bar(B_WEMPTY + ws), ((wn / K::WS) - 1) & 1);
+        mbar_expect_tx(bar(B_WFULL + ws), 128 * 128);
+        tma_load_2d(sW + ws * (128 * 128), m, bar(B_WFULL + ws), col, row);
+        ws ^= 1; ++wn;
+      };
+      for (int lt = 0; lt < T; ++lt) {
+        int img, h0, wc0;
+        tile_coords(t_begin + lt, img, h0, wc0);
+        const int xs = lt % K::XS;
+        if (lt >= K::XS) mbar_wait(bar(B_XEMPTY + xs), ((lt / K::XS) - 1) & 1);
+        TR(1, lt, 0);
+        mbar_expect_tx(bar(B_XFULL + xs), K::X_BYTES);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_5d(sX + xs * K::X_BYTES + kb * K::X_TILE, &mapX, bar(B_XFULL + xs), kb * 64, 0, h0, wc0, img);
+        if (C == 128) {
+          for (int ch = 0; ch < 3; ++ch)
+            for (int kb = 0; kb < KB; ++kb) wload(&mapWqkv, kb * 64, ch * 128);
+          if (lt > 0)
+            for (int kb = 0; kb < KB; ++kb) wload(&mapWproj, kb * 64, 0);
+        }
+      }
+      if (C == 128 && T > 0)
+        for (int kb = 0; kb < KB; ++kb) wload(&mapWproj, kb * 64, 0);
+    }
+  } else if (warp == 1) {
+    // =========================================== issuer G: qkv chunks + projection of the previous tile =================
+    const bool leader = elect_one();
+    TR_DECL(1);
+    const uint32_t idesc_qkv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_proj = idesc_qkv | (1u << 15);          // A = attention output, MN-major
+    int ws = 0;
+    uint32_t wn = 0;
+    if (C == 64) mbar_wait(bar(B_WRES), 0);
+    auto wwait = [&]() {                                          // next streamed weight stage -> its descriptor word
+      mbar_wait(bar(B_WFULL + ws), (wn / K::WS) & 1);
+      const uint32_t lo = (sW + ws * (128 * 128)) >> 4;
+      return lo;
+    };
+    auto wdone = [&]() {
+      if (leader) umma_commit(bar(B_WEMPTY + ws));
+      ws ^= 1; ++wn;
+    };
+    auto proj = [&](int lt) {
+      // TMEM slot 1 is used in the order k(0), k(1), proj(0), k(2), proj(1), ..., proj(T-1): its previous user is k(lt+1)
+      // (drained by the drain warps: ACCEMPTY[1] phase lt+1), or for the last tile proj(T-2) / k(0)
+      if (lt < T - 1) mbar_wait(bar(B_ACCEMPTY + 1), (lt + 1) & 1);
+      else if (T == 1) mbar_wait(bar(B_ACCEMPTY + 1), 0);
+      else mbar_wait(bar(B_PEMPTY), (T - 2) & 1);
+      mbar_wait(bar(B_ASREADY), lt & 1);
+      tc_fence_after();
+      TR(10, lt, 0);
+      const uint32_t tacc = tmem + C;
+      const uint32_t a_lo0 = (sA >> 4) | ((uint32_t)((C * 128) >> 4) << 16);       // LBO = next 64-pixel block
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t b_lo;
+        if (C == 128) { b_lo = wwait(); tc_fence_after(); } else b_lo = (sW + 192 * 128) >> 4;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lo2(tacc, a_lo0 + (uint32_t)((kb * 4 + k) * 128), hi, b_lo + 2 * k, hi, idesc_proj, (kb | k) != 0);
+        }
+        __syncwarp();
+        if (C == 128) wdone();
+      }
+      if (leader) umma_commit(bar(B_PFULL));
+      __syncwarp();
+      TR(11, lt, 0);
+    };
+    for (int lt = 0; lt < T; ++lt) {
+      const int xs = lt % K::XS;
+      mbar_wait(bar((XF ? B_XFDONE : B_XFULL) + xs), (lt / K::XS) & 1);
+      tc_fence_after();
+      TR(1, lt, 0);
+      for (int ch = 0; ch < 3; ++ch) {
+        const int slot = ch & 1;
+        if (slot == 0) {                 // slot 0: q(lt) = use 2 lt, v(lt) = use 2 lt + 1, one consumer (the drain warps)
+          const int n = 2 * lt + (ch >> 1);
+          if (n >= 1) mbar_wait(bar(B_ACCEMPTY + 0), (n - 1) & 1);
+        } else if (lt == 1) {            // slot 1 before k(1): k(0) drained
+          mbar_wait(bar(B_ACCEMPTY + 1), 0);
+        } else if (lt >= 2) {            // slot 1 before k(lt): proj(lt-2) drained by the epilogue warps
+          mbar_wait(bar(B_PEMPTY), (lt - 2) & 1);
+        }
+        tc_fence_after();
+        TR(2, lt, ch);
+        const uint32_t tacc = tmem + slot * C;
+        for (int kb = 0; kb < KB; ++kb) {
+          uint32_t b_lo;
+          if (C == 128) { b_lo = wwait(); tc_fence_after(); } else b_lo = (sW + ch * 64 * 128) >> 4;
+          const uint32_t a_lo = (sX + xs * K::X_BYTES + kb * K::X_TILE) >> 4;
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_lo(tacc, a_lo + 2 * k, b_lo + 2 * k, hi, idesc_qkv, (kb | k) != 0);
+          }
+          __syncwarp();
+          if (C == 128) wdone();
+        }
+        if (leader) umma_commit(bar(B_ACCFULL + slot));
+        __syncwarp();
+        TR(3, lt, ch);
+      }
+      if (leader) umma_commit(bar(B_XEMPTY + xs));
+      __syncwarp();
+      if (lt > 0) proj(lt - 1);
+    }
+    if (T > 0) proj(T - 1);
+  } else if (warp == 2) {
+    // =========================================== issuer A: S = Qh^T Kh and O = P V per unit ================================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_pv = (1u << 4) | ((uint32_t)(K::NPV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // fp16 x fp16
+    constexpr uint32_t QK_LBO = C == 64 ? 2048 : 8 * 2048;       // next 64 rows of M / N: the pair's other window / the next channel block
+    constexpr uint32_t UNIT_Q = C == 64 ? 2 * 2048 : 2048;       // bytes of q / k per unit
+    constexpr uint32_t UNIT_V = C == 64 ? 2 * 3072 : 3072;
+    uint32_t gu = 0;
+    TR_DECL(2);
+    auto pv = [&](int lt, int u, uint32_t g) {
+      const uint32_t b = g & 1;
+      if (u == 0) mbar_wait(bar(B_VREADY), lt & 1);
+      mbar_wait(bar(B_PREADY + b), (g >> 1) & 1);
+      tc_fence_after();
+      TR(4, lt, u);
+      if (leader) {
+        const uint32_t scol = tmem + K::SCOL0 + b * 128;
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks) {
+          const uint32_t b_lo = (sV + (ks >> 2) * K::V_KB + u * UNIT_V + (ks & 3) * 32) >> 4;
+          umma_ts_lo(scol + K::OOFF, scol + ks * 8, b_lo, hi, idesc_pv, ks != 0);
+        }
+        umma_commit(bar(B_OFULL + b));
+      }
+      __syncwarp();
+    };
+    for (int lt = 0; lt < T; ++lt) {
+      mbar_wait(bar(B_QKREADY), lt & 1);
+      tc_fence_after();
+      TR(1, lt, 0);
+      for (int u = 0; u < UNITS; ++u, ++gu) {
+        const uint32_t b = gu & 1;
+        if (gu >= 2) { mbar_wait(bar(B_OEMPTY + b), ((gu >> 1) - 1) & 1); tc_fence_after(); }
+        TR(2, lt, u);
+        if (leader) {
+          const uint32_t a_lo = ((sQ + u * UNIT_Q) >> 4) | ((QK_LBO >> 4) << 16);
+          const uint32_t b_lo = ((sK + u * UNIT_Q) >> 4) | ((QK_LBO >> 4) << 16);
+          umma_bf16_lo(tmem + K::SCOL0 + b * 128, a_lo, b_lo, hi, idesc_s, false);
+          umma_commit(bar(B_SFULL + b));
+        }
+        __syncwarp();
+        if (u >= 1) pv(lt, u - 1, gu - 1);
+      }
+      pv(lt, UNITS - 1, gu - 1);
+      if (leader) umma_commit(bar(B_OPSFREE));
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================================== drain: q / k / v accumulators -> operand tiles ==========================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;               // tile row = pixel: window r >> 4, pixel-in-window r & 15
+    const int w = r >> 4, px = r & 15;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t row_off = (uint32_t)(w * 2048 + (px >> 3) * 1024 + (px & 7) * 128);       // inside a q / k mn-block
+    const uint32_t vrow_off = (uint32_t)(w * 3072 + (px >> 3) * 1024 + (px & 7) * 128);      // inside a v K block
+    const int sw = px & 7;
+    TR_DECL(3 + q);
+    for (int lt = 0; lt < T; ++lt) {
+#pragma unroll 1
+      for (int ch = 0; ch < 3; ++ch) {
+        const int slot = ch & 1;
+        const uint32_t par = slot == 0 ? (uint32_t)(ch >> 1) : (uint32_t)(lt & 1);     // slot 0: q, v alternate; slot 1: k(lt) is phase lt
+        mbar_wait(bar(B_ACCFULL + slot), par);
+        tc_fence_after();
+        TR(1, lt, ch);
+        const uint32_t tacc = tmem + slot * C + lane_addr;
+        const float* bs = sbias + ch * C;
+        if (ch < 2) {
+          float ss = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            float v[32];
+            tmem_ld32_sync(tacc + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float t = v[j] + bs[c0 + j]; ss = fmaf(t, t, ss); }
+          }
+          // F.normalize: x / max(|x|, 1e-12); k also carries log2(e) so the softmax exponential is a bare ex2
+          const float rn = rsqrtf(fmaxf(ss, 1e-24f)) * (ch == 1 ? 1.4426950408889634f : 1.f);
+          TR(2, lt, ch);
+          if (ch == 0 && lt > 0) mbar_wait(bar(B_OPSFREE), (lt - 1) & 1);   // the previous tile's MMAs have finished reading q, k, v
+          TR(3, lt, ch);
+          uint8_t* dst0 = gen + (ch == 0 ? K::OFF_Q : K::OFF_K) + row_off;
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            float v[32];
+            tmem_ld32_sync(tacc + c0, v);
+            if (c0 + 32 >= C) {                   // last read of this accumulator slot
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + slot));
+            }
+            uint8_t* dst = dst0 + (c0 >> 6) * (8 * 2048);
+            const int cc0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = pack_bf16x2_rn((v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e]) * rn, (v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]) * rn);
+              *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (ch == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_QKREADY));
+          }
+          TR(4, lt, ch);
+        } else {
+          uint8_t* dst0 = gen + K::OFF_V + vrow_off;
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            float v[32];
+            tmem_ld32_sync(tacc + c0, v);
+            if (c0 + 32 >= C) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + slot));
+            }
+            uint8_t* dst = dst0 + (c0 >> 6) * K::V_KB;
+            const int cc0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = pack_f16x2_rn(v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e], v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_VREADY));
+          TR(4, lt, ch);
+        }
+      }
+    }
+  } else if (warp >= 8 && warp < 8 + 4 * NSM) {
+    // =========================================== softmax: S -> P = exp2(S) (fp16) in place =================================
+    const int q = warp & 3;
+    const int grp = (warp - 8) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t total_units = (uint32_t)T * UNITS;
+    TR_DECL(7 + grp * 4 + q);
+    for (uint32_t gu = (NSM == 2 ? grp : 0); gu < total_units; gu += NSM) {
+      const uint32_t b = gu & 1;
+      mbar_wait(bar(B_SFULL + b), (gu >> 1) & 1);
+      tc_fence_after();
+      TR(1, gu / UNITS, gu % UNITS);
+      const uint32_t sbuf = tmem + K::SCOL0 + b * 128 + lane_addr;
+      const uint32_t scol = sbuf + (C == 64 ? 64 * (q >> 1) : 0);     // C=64: lanes 64-127 hold the pair's second window in columns 64-127
+      uint32_t pk[32];
+#pragma unroll
+      for (int kc = 0; kc < C / 32; ++kc) {
+        float v[32];
+        tmem_ld32_sync(scol + kc * 32, v);
+        TR(5, gu / UNITS, kc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t x = pack_f16x2_rn(v[2 * j], v[2 * j + 1]);
+          pk[(kc & 1) * 16 + j] = (j & 1) ? la::exp2_poly_f16x2(x) : la::ex2_f16x2(x);
+        }
+        if (kc & 1) tmem_st32(sbuf + (kc >> 1) * 32, pk);
+        TR(6, gu / UNITS, kc);
+      }
+      tmem_st_wait();
+      TR(7, gu / UNITS, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PREADY + b));
+      TR(2, gu / UNITS, gu % UNITS);
+    }
+  } else if (warp >= 8 + 4 * NSM && warp < 12 + 4 * NSM) {
+    // =========================================== O drain + projection epilogue ==========================================
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane;
+    bool store_pending = false;
+    uint32_t gu = 0;
+    TR_DECL(15 + q);
+    for (int lt = 0; lt < T; ++lt) {
+      // the staging of the previous tile's TMA stores aliases the A-operand tile: drain the reads, then the whole group may write
+      if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      for (int u = 0; u < UNITS; ++u, ++gu) {
+        const uint32_t b = gu & 1;
+        mbar_wait(bar(B_OFULL + b), (gu >> 1) & 1);
+        tc_fence_after();
+        TR(1, lt, u);
+        float v[32];
+        tmem_ld32_sync(tmem + K::SCOL0 + b * 128 + K::OOFF + (C == 64 ? 24 * (q >> 1) : 0) + lane_addr, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_OEMPTY + b));
+        const float inv = __fdividef(1.f, v[16]);               // row sum of P (in [C/e^1.5, C e^1.5]) from the ones rows
+        const int win = C == 64 ? 2 * u + (q >> 1) : u;         // window of this thread's row
+        const int i = C == 64 ? 32 * (q & 1) + lane : r;        // channel of this thread's row
+        uint8_t* dst = gen + K::OFF_A + (win >> 2) * (C * 128) + i * 128;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) o[k2] = pack_bf16x2_rn(v[e * 8 + 2 * k2] * inv, v[e * 8 + 2 * k2 + 1] * inv);
+          *reinterpret_cast<uint4*>(dst + (((2 * (win & 3) + e) ^ (i & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_ASREADY));
+      TR(2, lt, 0);
+      // ---- projection accumulators of this tile (slot 1): + bias -> bf16 -> swizzled staging -> TMA store
+      mbar_wait(bar(B_PFULL), lt & 1);
+      tc_fence_after();
+      TR(3, lt, 0);
+      const float* bs = sbias + 3 * C;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32];
+        tmem_ld32_sync(tmem + C + c0 + lane_addr, v);
+        if (c0 + 32 >= C) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_PEMPTY));
+        }
+        uint8_t* dst = gen + K::OFF_A + (c0 >> 6) * K::X_TILE + r * 128;
+        const int cc0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = pack_bf16x2_rn(v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e], v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        int img, h0, wc0;
+        tile_coords(t_begin + lt, img, h0, wc0);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_store_5d(&mapOut, sA + kb * K::X_TILE + q * 4096, kb * 64, 0, h0, wc0 + 2 * q, img);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        store_pending = true;
+      }
+      TR(4, lt, 0);
+    }
+    if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (XF && warp >= 12 + 4 * NSM) {
+    // =========================================== fused input InstanceNorm + activation (as conv_tma.cu) ===================
+    const int xt = tid - 32 * (12 + 4 * NSM);          // 0..127
+    const int pchunk = xt & 7, rbase = xt >> 3;
+    const int lchunk = pchunk ^ (rbase & 7);
+    const double inv_hw = 1.0 / ((double)p.H * (double)p.W);
+    const bool relu = p.in_act == MSG_ACT_RELU;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    int cur_img = -1;
+    for (int lt = 0; lt < T; ++lt) {
+      const int img = (t_begin + lt) / p.tiles_per_img;
+      if (img != cur_img) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int ci = xt; ci < C; ci += 128) {
+          const double* st = p.in_stats + ((size_t)img * C + ci) * 2;
+          float mean, rstd;
+          finalize_stats(st[0], st[1], inv_hw, mean, rstd);
+          xf_tab[ci] = rstd;
+          xf_tab[C + ci] = 0.f - mean * rstd;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        cur_img = img;
+      }
+      const int xs = lt % K::XS;
+      mbar_wait(bar(B_XFULL + xs), (lt / K::XS) & 1);
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = xf_tab[kb * 64 + lchunk * 8 + e]; sh[e] = xf_tab[C + kb * 64 + lchunk * 8 + e]; }
+        uint8_t* tile = gen + K::OFF_X + xs * K::X_BYTES + kb * K::X_TILE + rbase * 128 + pchunk * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4* ptr = reinterpret_cast<uint4*>(tile + i * (16 * 128));
+          uint4 raw = *ptr;
+          uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 x2 = make_float2(__uint_as_float(w4[j] << 16), __uint_as_float(w4[j] & 0xffff0000u));
+            const float2 o2 = __ffma2_rn(x2, make_float2(sc[2 * j], sc[2 * j + 1]), make_float2(sh[2 * j], sh[2 * j + 1]));
+            __nv_bfloat162 pk = __floats2bfloat162_rn(o2.x, o2.y);
+            if (relu) pk = __hmax2(pk, zero2);
+            w4[j] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          *ptr = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_XFDONE + xs));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+unsigned long long* g_trace = nullptr;
+
+template <int C, int NSM, bool XF>
+int launch(const CUtensorMap& mX, const CUtensorMap& mQ, const CUtensorMap& mP, const CUtensorMap& mO, const LaParams& p, cudaStream_t st) {
+  static DeviceOnce attr_set;
+  if (attr_set.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(la_stage_kernel<C, NSM, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM);
+    MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "la_stage: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set.done();
+  }
+  int grid = sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  la_stage_kernel<C, NSM, XF><<<grid, 32 * (12 + 4 * NSM + (XF ? 4 : 0)), Cfg<C>::SMEM, st>>>(mX, mQ, mP, mO, p);
+  return check_launch("la_stage_kernel");
+}
+
+}  // namespace
+
+bool la_stage_supported(int dtype, int N, int H, int W, int C, const void* x, const void* wqkv, const void* wproj, const void* out) {
+  if (dtype != MSG_BF16) return false;
+  if (C != 64 && C != 128) return false;
+  if (N <= 0 || H <= 0 || W <= 0 || (H & 3) || (W & 3)) return false;
+  if (((uintptr_t)x | (uintptr_t)wqkv | (uintptr_t)wproj | (uintptr_t)out) & 15) return false;
+  const long long tiles = (long long)N * (H / 4) * ((W + 31) / 32);
+  if (tiles > 0x3fffffffLL) return false;
+  return get_encode() != nullptr;
+}
+
+int la_stage_fwd(const void* x, const double* in_stats, int in_act, const void* wqkv, const float* bqkv, const void* wproj,
+                 const float* bproj, int N, int H, int W, int C, void* out, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  MSG_REQUIRE(enc != nullptr, MSG_ERR_CUDA, "la_stage: cuTensorMapEncodeTiled unavailable");
+  LaParams p;
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = (W + 31) / 32;
+  p.tiles_per_img = (H / 4) * p.tiles_w;
+  p.total_tiles = N * p.tiles_per_img;
+  p.bqkv = bqkv; p.bproj = bproj; p.in_stats = in_stats; p.in_act = in_act;
+  p.trace = g_trace;
+  CUtensorMap mX, mO, mQ, mP;
+  for (int which = 0; which < 2; ++which) {
+    // (channel, x in window, y, window column, image): a box lands as [window][y in window][x in window][64 ch]
+    cuuint64_t dims[5] = {(cuuint64_t)C, 4, (cuuint64_t)H, (cuuint64_t)(W / 4), (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)4 * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {64, 4, 4, which == 0 ? 8u : 2u, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &mX : &mO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, which == 0 ? (void*)x : out, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     which == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "la_stage: cuTensorMapEncodeTiled(%s) failed with %d", which == 0 ? "x" : "out", (int)r);
+  }
+  for (int which = 0; which < 2; ++which) {
+    const int rows = which == 0 ? 3 * C : C;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(C == 64 ? rows : 128)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(which == 0 ? &mQ : &mP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, which == 0 ? (void*)wqkv : (void*)wproj, dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "la_stage: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+  }
+  const char* env = getenv("MSG_LA_SOFTMAX_GROUPS");      // (read per call: the tests switch it)
+  const int env_nsm = env ? atoi(env) : 0;
+  const bool xf = in_stats != nullptr;
+  const int nsm = env_nsm == 1 || env_nsm == 2 ? env_nsm : 2;
+  if (C == 64) {
+    if (nsm == 2) return xf ? launch<64, 2, true>(mX, mQ, mP, mO, p, st) : launch<64, 2, false>(mX, mQ, mP, mO, p, st);
+    return xf ? launch<64, 1, true>(mX, mQ, mP, mO, p, st) : launch<64, 1, false>(mX, mQ, mP, mO, p, st);
+  }
+  if (nsm == 2) return xf ? launch<128, 2, true>(mX, mQ, mP, mO, p, st) : launch<128, 2, false>(mX, mQ, mP, mO, p, st);
+  return xf ? launch<128, 1, true>(mX, mQ, mP, mO, p, st) : launch<128, 1, false>(mX, mQ, mP, mO, p, st);
+}
+
+}  // namespace msg
+
+using namespace msg;
+
+/* development hook (MSG_LA_TRACE builds): device buffer of 19 x 4096 u64 receiving CTA 0's role timelines; NULL = off */
+extern "C" int msg_la_stage_set_trace(void* buf) {
+  g_trace = reinterpret_cast<unsigned long long*>(buf);
+  return MSG_OK;
+}
+
+extern "C" int msg_la_stage_supported(int dtype, int N, int H, int W, int C, const void* x, const void* wqkv, const void* wproj,
+                                      const void* out) {
+  return la_stage_supported(dtype, N, H, W, C, x, wqkv, wproj, out) ? 1 : 0;
+}
+
+extern "C" int msg_la_stage_fwd(int dtype, const void* x, const double* in_stats, int in_act, const void* wqkv, const float* bqkv,
+                                const void* wproj, const float* bproj, int N, int H, int W, int C, void* out, void* stream) {
+  MSG_REQUIRE(x && wqkv && bqkv && wproj && bproj && out, MSG_ERR_SHAPE, "la_stage: null pointer");
+  MSG_REQUIRE(la_stage_supported(dtype, N, H, W, C, x, wqkv, wproj, out), MSG_ERR_UNSUPPORTED,
+              "la_stage: needs bf16, C in {64, 128}, H and W multiples of 4, 16-byte aligned pointers (got C=%d, %dx%d)", C, H, W);
+  MSG_REQUIRE(in_stats == nullptr || in_act == MSG_ACT_NONE || in_act == MSG_ACT_RELU, MSG_ERR_UNSUPPORTED,
+              "la_stage: fused input norm supports ReLU / no activation");
+  return la_stage_fwd(x, in_stats, in_act, wqkv, bqkv, wproj, bproj, N, H, W, C, out, as_stream(stream));
+}

@@ -81,6 +81,7 @@ class GeneratorEngine:
         self.convT_slab = os.environ.get("MSG_CONVT_SLAB", "1") == "1"
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
+        self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
 
     def _versions(self, params, names):
         return tuple((params[n].data_ptr(), params[n]._version) for n in names)
@@ -158,6 +159,14 @@ class GeneratorEngine:
         else:
             y0 = g[f"{s}.0"].forward(a_in, self._packed(P, f"{s}.0", "fwd", dtype), self._bias(P, f"{s}.0"), stats=st0)
         wq = self._packed(P, f"{s}.3.qkv", "fwd", dtype)
+        wp = self._packed(P, f"{s}.3.proj", "fwd", dtype)
+        if not keep and self.fuse_la and ops.la_stage_supported(y0, wq, wp):
+            # inference, C in {64, 128}: the whole LocalAttention stage -- IN + ReLU of y0 on the landed tile, qkv 1x1, window
+            # attention with S / P in tensor memory, proj 1x1 -- is ONE tcgen05 launch; qkv and the attention output never
+            # exist in HBM (csrc/la_stage.cu)
+            a1 = ops.la_stage_fwd(y0, wq, self._bias(P, f"{s}.3.qkv"), wp, self._bias(P, f"{s}.3.proj"), in_stats=st0, in_act=ACT_RELU)
+            del y0
+            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C)
         if not keep and self.fuse_in_norm and g[f"{s}.3.qkv"].fused_in_norm_ok(y0, wq):
             # inference: ReLU(IN(y0)) has ONE consumer, the 1x1 qkv conv (LocalAttention has no residual), so the
             # conv normalises its A tiles in shared memory and the normalised tensor never exists in HBM
@@ -169,9 +178,15 @@ class GeneratorEngine:
         att = ops.local_attn_fwd(qkv)
         if not keep:
             del y0, a0, qkv
-        a1 = g[f"{s}.3.proj"].forward(att, self._packed(P, f"{s}.3.proj", "fwd", dtype), self._bias(P, f"{s}.3.proj"))
+        a1 = g[f"{s}.3.proj"].forward(att, wp, self._bias(P, f"{s}.3.proj"))
         if not keep:
             del att
+            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C)
+        return self._msb_fwd(P, s, a1, dict(a_in=a_in, y0=y0, st0=st0, a0=a0, qkv=qkv, att=att), dtype, keep, arena, g, C)
+
+    def _msb_fwd(self, P, s, a1, saved, dtype, keep, arena, g, C):
+        """MultiScaleBlock of stage s on a1 (enhanced_generator.py:78-84)."""
+        dev = a1.device
         b = torch.empty_like(a1)
         stb = arena.take(C)
         if self.use_slab and dtype == torch.bfloat16 and C in self._msb_prog and a1.shape[2] % 8 == 0:
@@ -203,7 +218,7 @@ class GeneratorEngine:
         a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1, out=None if keep else f)
         if not keep:
             return a2, None
-        saved = dict(a_in=a_in, y0=y0, st0=st0, a0=a0, qkv=qkv, att=att, a1=a1, b=b, stb=stb, bn=bn, f=f, stf=stf)
+        saved.update(a1=a1, b=b, stb=stb, bn=bn, f=f, stf=stf)
         return a2, saved
 
     def encode(self, P, x, dtype, save):

@@ -286,6 +286,27 @@ def local_attn_bwd(qkv, dout, ws=4):
     return dqkv
 
 
+def la_stage_supported(x, wqkv, wproj):
+    """True when the fused LocalAttention stage kernel (csrc/la_stage.cu) takes this input: bf16, C in {64, 128}."""
+    if x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    N, H, W, C = x.shape
+    return _lib.load().msg_la_stage_supported(_dt(x), N, H, W, C, _p(x), _p(wqkv), _p(wproj), _p(x)) == 1
+
+
+def la_stage_fwd(x, wqkv, bqkv, wproj, bproj, in_stats=None, in_act=ACT_NONE, out=None):
+    """LocalAttention.forward (enhanced_generator.py:13-47) in one launch: [IN + act of the producer] -> qkv 1x1 ->
+    4x4-window channel attention -> proj 1x1.  x: [N,H,W,C] bf16 (raw conv output with `in_stats`, else normalised);
+    wqkv / wproj: packed bf16 1x1 weights ([3C][C], [C][C]); biases fp32."""
+    _dev(x)
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("msg_la_stage_fwd", _dt(x), _p(x), _p(in_stats), in_act, _p(wqkv), _p(bqkv), _p(wproj), _p(bproj), N, H, W, C,
+              _p(out), _stream())
+    return out
+
+
 # ---- layout / blend ------------------------------------------------------------------------------
 def nchw_to_nhwc(x, dtype, Cp=None):
     _dev(x)

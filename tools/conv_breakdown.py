@@ -39,6 +39,8 @@ def main():
                 key = f"{name} Cin={d.Cin} Ntot={d.Ntot} taps={d.n_taps} plane={d.H}x{d.W}"
             elif hasattr(d, "n_groups"):
                 key = f"{name} Cin={d.Cin} Ntot={d.Ntot} kblocks={d.n_kblocks} plane={d.H}x{d.W}"
+        if name == "msg_la_stage_fwd":
+            key = f"{name} C={args[11]} plane={args[9]}x{args[10]}"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = orig_call(name, *args)
