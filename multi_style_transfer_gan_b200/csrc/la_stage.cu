@@ -47,7 +47,9 @@ struct Cfg {
   static constexpr int KB = C / 64;                    // 64-channel blocks
   static constexpr int UNITS = C == 64 ? 4 : 8;        // attention units per tile: window pairs (C=64) / windows (C=128)
   static constexpr int NPV = C == 64 ? 48 : 32;        // N of the P.V MMA: [16 px | 8 ones] per window (+ 8 don't-care at C=128)
-  static constexpr int XS = C == 64 ? 2 : 1;           // x-tile stages
+  static constexpr int NBUF = C == 64 ? 3 : 2;         // S / P / O buffers in tensor memory (units in flight)
+  static constexpr int NSET = C == 64 ? 2 : 1;         // q / k / v operand sets in shared memory (tiles in flight)
+  static constexpr int XS = C == 64 ? 2 : 1;           // x-tile stages (a consumed stage doubles as the output staging)
   static constexpr int WS = 2;                         // streamed-weight stages (C=128)
   static constexpr int X_TILE = 128 * 128;             // one K block of an x tile: 128 pixel rows x 128 B
   static constexpr int X_BYTES = KB * X_TILE;
@@ -55,21 +57,25 @@ struct Cfg {
   static constexpr int W_BYTES = C == 64 ? (192 + 64) * 128 : WS * 128 * 128;
   static constexpr int OFF_W = OFF_X + XS * X_BYTES;
   static constexpr int QK_BYTES = KB * 8 * 2048;       // [mn block][window][16 pixel rows x 128 B]
-  static constexpr int OFF_Q = OFF_W + W_BYTES;
-  static constexpr int OFF_K = OFF_Q + QK_BYTES;
   static constexpr int V_KB = 8 * 3072;                // per K block: [window][16 pixel rows + 8 ones rows][128 B]
-  static constexpr int OFF_V = OFF_K + QK_BYTES;
-  static constexpr int V_BYTES = KB * V_KB + 1024;     // + the 4th (don't-care) row group of the last window
-  static constexpr int OFF_A = OFF_V + V_BYTES;        // attention output = A of the projection; later the store staging
-  static constexpr int A_BYTES = KB * 128 * 128;
-  static constexpr int OFF_BIAS = OFF_A + A_BYTES;     // 3C qkv biases + C proj biases (fp32)
+  static constexpr int V_BYTES = KB * V_KB;
+  static constexpr int SET_BYTES = 2 * QK_BYTES + V_BYTES;     // q | k | v of one tile
+  static constexpr int OFF_SET = OFF_W + W_BYTES;
+  static constexpr int OFF_A = OFF_SET + NSET * SET_BYTES + 1024;   // (+ the don't-care 4th row group of the last window at C=128)
+  static constexpr int A_BYTES = KB * 128 * 128;       // attention output = A operand of the projection
+  // output staging of the epilogue: at C=128 (one x stage, no spare smem) it aliases the x stage, which the qkv GEMMs of
+  // the NEXT tile have consumed by the time the projection completes; at C=64 it is its own region
+  static constexpr bool STG_ALIAS_X = C == 128;
+  static constexpr int OFF_STG = STG_ALIAS_X ? OFF_X : OFF_A + A_BYTES;
+  static constexpr int OFF_BIAS = OFF_A + A_BYTES + (STG_ALIAS_X ? 0 : A_BYTES);     // 3C qkv biases + C proj biases (fp32)
   static constexpr int OFF_XF = OFF_BIAS + 4 * C * 4;  // fused input norm: scale[C], shift[C]
   static constexpr int OFF_BAR = OFF_XF + 2 * C * 4;
   static constexpr int SMEM = OFF_BAR + 512 + 1024;    // + alignment slack
   static constexpr int SCOL0 = 2 * C;                  // first S buffer column
   static constexpr int OOFF = C / 2;                   // O columns inside an S buffer
-  static_assert(OFF_A % 1024 == 0 && OFF_V % 1024 == 0 && OFF_Q % 1024 == 0, "operand tiles must be 1024-byte aligned");
+  static_assert(OFF_A % 1024 == 0 && OFF_SET % 1024 == 0 && SET_BYTES % 1024 == 0, "operand tiles must be 1024-byte aligned");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(SCOL0 + NBUF * 128 <= 512, "tensor memory budget");
 };
 
 struct LaParams {
@@ -83,7 +89,7 @@ struct LaParams {
 };
 
 #ifdef MSG_LA_TRACE
-// timeline instrumentation (development builds: python -m multi_style_transfer_gan_b200.build with MSG_LA_TRACE=1):
+// timeline instrumentation (development builds: MSG_LA_TRACE=1 python -m multi_style_transfer_gan_b200.build):
 // lane 0 of each role of CTA 0 appends (event, tile, unit, clock64) -- read back with tools/la_trace.py
 #define TR_DECL(role) unsigned long long* tr_ = (p.trace && blockIdx.x == 0 && lane == 0) ? p.trace + (role) * 4096 : nullptr; int tr_n = 0
 #define TR(ev, lt_, u_) do { if (tr_ && tr_n < 2047) { tr_[2 * tr_n] = ((unsigned long long)(ev) << 32) | ((unsigned long long)(lt_) << 8) | (unsigned long long)(u_); tr_[2 * tr_n + 1] = clock64(); ++tr_n; tr_[4094] = tr_n; } } while (0)
@@ -93,11 +99,17 @@ struct LaParams {
 #endif
 
 enum Bar {
-  B_XFULL = 0, B_XEMPTY = 2, B_XFDONE = 4, B_WFULL = 6, B_WEMPTY = 8, B_WRES = 10, B_ACCFULL = 11, B_ACCEMPTY = 13,
-  B_QKREADY = 15, B_VREADY = 16, B_OPSFREE = 17, B_SFULL = 18, B_PREADY = 20, B_OFULL = 22, B_OEMPTY = 24, B_ASREADY = 26,
-  B_PFULL = 27, B_PEMPTY = 28,      // projection accumulators (TMEM slot 1, shared with k): their own barriers, because a parity wait only
-                                    // separates ADJACENT phases and slot 1 has two consumers (drain warps: k; epilogue warps: proj)
-  B_COUNT = 29
+  B_XFULL = 0, B_XEMPTY = 2, B_XFDONE = 4, B_WFULL = 6, B_WEMPTY = 8, B_WRES = 10,
+  B_ACCFULL = 11, B_ACCEMPTY = 13,      // accumulator ring: slot 0 = q, v (in that order, one consumer); slot 1 = k
+  B_PFULL = 15, B_PEMPTY = 16,          // projection accumulators (TMEM slot 1, shared with k): their own barriers, because a parity wait
+                                        // only separates ADJACENT phases and slot 1 has two consumers (drain warps: k; epilogue warps: proj)
+  B_STFREE = 17,                        // the output staging (= a consumed x stage) has been read by the TMA stores
+  B_ASREADY = 18,                       // attention output of a tile complete in smem (8 softmax / O-drain warps)
+  B_VREADY = 19,                        // [set]
+  B_QKREADY = 21,                       // [set][drain warp]: q and k rows of that warp's two windows written
+  B_WINFREE = 29,                       // [set][drain warp]: the MMAs reading that warp's windows (S and P.V) have completed
+  B_SFULL = 37, B_PREADY = 40, B_OFULL = 43, B_OEMPTY = 46,      // [S buffer]
+  B_COUNT = 49
 };
 
 __device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
@@ -108,19 +120,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// v[0..32) += bias[0..32): 8 LDS.128 (every lane reads the same address: broadcast) + 16 packed adds
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* bs) {
+  const float4* b4 = reinterpret_cast<const float4*>(bs);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = b4[j];
+    const float2 lo = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b.x, b.y));
+    const float2 hi2 = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w));
+    v[4 * j] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi2.x; v[4 * j + 3] = hi2.y;
+  }
+}
 
-template <int C, int NSM, bool XF>
-__global__ void __launch_bounds__(32 * (12 + 4 * NSM + (XF ? 4 : 0)), 1)
+template <int C, bool XF>
+__global__ void __launch_bounds__(32 * (12 + 4 * Cfg<C>::NBUF + (XF ? 4 : 0)), 1)
 la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWqkv,
                 const __grid_constant__ CUtensorMap mapWproj, const __grid_constant__ CUtensorMap mapOut, const LaParams p) {
   using K = Cfg<C>;
-  constexpr int KB = K::KB, UNITS = K::UNITS;
+  constexpr int KB = K::KB, UNITS = K::UNITS, NBUF = K::NBUF, NSET = K::NSET, XS = K::XS;
+  constexpr int EP0 = 8 + 4 * NBUF;          // first epilogue warp (after the NBUF softmax groups)
+  constexpr int XF0 = EP0 + 4;               // first transform warp
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sX = base + K::OFF_X, sW = base + K::OFF_W, sQ = base + K::OFF_Q, sK = base + K::OFF_K, sV = base + K::OFF_V,
-                 sA = base + K::OFF_A, sBar = base + K::OFF_BAR;
+  const uint32_t sX = base + K::OFF_X, sW = base + K::OFF_W, sSet = base + K::OFF_SET, sA = base + K::OFF_A, sBar = base + K::OFF_BAR;
   float* sbias = reinterpret_cast<float*>(gen + K::OFF_BIAS);
   float* xf_tab = reinterpret_cast<float*>(gen + K::OFF_XF);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + K::OFF_BAR + 8 * B_COUNT);
@@ -129,9 +153,10 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   // ---- one-time setup
   for (int i = tid; i < 4 * C; i += (int)blockDim.x) sbias[i] = i < 3 * C ? p.bqkv[i] : p.bproj[i - 3 * C];
   // the all-ones row group of every window of V (fp16 1.0): P.[ones] = softmax row sums, accumulated in fp32 by the MMA
-  for (int i = tid; i < KB * 8 * 64; i += (int)blockDim.x) {
-    const int kb = i / (8 * 64), w = (i / 64) & 7, c16 = i & 63;
-    *reinterpret_cast<uint4*>(gen + K::OFF_V + kb * K::V_KB + w * 3072 + 2048 + c16 * 16) =
+  for (int i = tid; i < NSET * KB * 8 * 64; i += (int)blockDim.x) {
+    const int set = i / (KB * 8 * 64), r = i - set * (KB * 8 * 64);
+    const int kb = r / (8 * 64), w = (r / 64) & 7, c16 = r & 63;
+    *reinterpret_cast<uint4*>(gen + K::OFF_SET + set * K::SET_BYTES + 2 * K::QK_BYTES + kb * K::V_KB + w * 3072 + 2048 + c16 * 16) =
         make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
   }
   if (warp == 1) {
@@ -140,11 +165,14 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         mbar_init(bar(B_XFULL + s), 1); mbar_init(bar(B_XEMPTY + s), 1); mbar_init(bar(B_XFDONE + s), 4);
         mbar_init(bar(B_WFULL + s), 1); mbar_init(bar(B_WEMPTY + s), 1);
         mbar_init(bar(B_ACCFULL + s), 1); mbar_init(bar(B_ACCEMPTY + s), 4);
-        mbar_init(bar(B_SFULL + s), 1); mbar_init(bar(B_PREADY + s), 4);
-        mbar_init(bar(B_OFULL + s), 1); mbar_init(bar(B_OEMPTY + s), 4);
+        mbar_init(bar(B_VREADY + s), 4);
       }
-      mbar_init(bar(B_WRES), 1); mbar_init(bar(B_QKREADY), 4); mbar_init(bar(B_VREADY), 4); mbar_init(bar(B_OPSFREE), 1);
-      mbar_init(bar(B_ASREADY), 4); mbar_init(bar(B_PFULL), 1); mbar_init(bar(B_PEMPTY), 4);
+      for (int s = 0; s < 8; ++s) { mbar_init(bar(B_QKREADY + s), 1); mbar_init(bar(B_WINFREE + s), 1); }
+      for (int s = 0; s < 3; ++s) {
+        mbar_init(bar(B_SFULL + s), 1); mbar_init(bar(B_PREADY + s), 4); mbar_init(bar(B_OFULL + s), 1); mbar_init(bar(B_OEMPTY + s), 4);
+      }
+      mbar_init(bar(B_WRES), 1); mbar_init(bar(B_PFULL), 1); mbar_init(bar(B_PEMPTY), 4); mbar_init(bar(B_STFREE), 4);
+      mbar_init(bar(B_ASREADY), 4 * NBUF);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -178,12 +206,12 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
+      TR_DECL(0);
       if (C == 64) {
         mbar_expect_tx(bar(B_WRES), (192 + 64) * 128);
         tma_load_2d(sW, &mapWqkv, bar(B_WRES), 0, 0);
         tma_load_2d(sW + 192 * 128, &mapWproj, bar(B_WRES), 0, 0);
       }
-      TR_DECL(0);
       int ws = 0;
       uint32_t wn = 0;                                   // weight loads issued
       auto wload = [&](const CUtensorMap* m, int col, int row) {
@@ -195,8 +223,12 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       for (int lt = 0; lt < T; ++lt) {
         int img, h0, wc0;
         tile_coords(t_begin + lt, img, h0, wc0);
-        const int xs = lt % K::XS;
-        if (lt >= K::XS) mbar_wait(bar(B_XEMPTY + xs), ((lt / K::XS) - 1) & 1);
+        const int xs = lt % XS;
+        if (lt >= XS) mbar_wait(bar(B_XEMPTY + xs), ((lt / XS) - 1) & 1);
+        // C=128: the stage was the output staging of tile lt - 2, whose TMA stores must have finished reading it (the epilogue of
+        // tile lt - 1 cannot have completed yet -- its projection is issued after the qkv GEMMs of THIS tile -- so the parity
+        // wait is on an adjacent phase)
+        if (K::STG_ALIAS_X && lt >= 2) mbar_wait(bar(B_STFREE), (lt - 2) & 1);
         TR(1, lt, 0);
         mbar_expect_tx(bar(B_XFULL + xs), K::X_BYTES);
         for (int kb = 0; kb < KB; ++kb)
@@ -256,8 +288,8 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       TR(11, lt, 0);
     };
     for (int lt = 0; lt < T; ++lt) {
-      const int xs = lt % K::XS;
-      mbar_wait(bar((XF ? B_XFDONE : B_XFULL) + xs), (lt / K::XS) & 1);
+      const int xs = lt % XS;
+      mbar_wait(bar((XF ? B_XFDONE : B_XFULL) + xs), (lt / XS) & 1);
       tc_fence_after();
       TR(1, lt, 0);
       for (int ch = 0; ch < 3; ++ch) {
@@ -293,56 +325,66 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       if (lt > 0) proj(lt - 1);
     }
     if (T > 0) proj(T - 1);
-  } else if (warp == 2) {
-    // =========================================== issuer A: S = Qh^T Kh and O = P V per unit ================================
+  } else if (warp == 2 || warp == 3) {
+    // =========================================== issuers A: S = Qh^T Kh (warp 2) and O = P V (warp 3) per unit =====================
+    // Two issuing warps, each an in-order stream with blocking (hardware-suspended) barrier waits: S(g) goes out as soon as
+    // buffer g % NBUF is free and the unit's q / k rows are written; P.V(g) as soon as its softmax is done -- neither stream can
+    // hold back the other (one in-order issuer stalled the P.V products of a tile behind the S of the next one; a polling issuer
+    // burns the issue slots of the scheduler it shares with a quarter of the softmax warps).
     const bool leader = elect_one();
     const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_pv = (1u << 4) | ((uint32_t)(K::NPV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // fp16 x fp16
     constexpr uint32_t QK_LBO = C == 64 ? 2048 : 8 * 2048;       // next 64 rows of M / N: the pair's other window / the next channel block
     constexpr uint32_t UNIT_Q = C == 64 ? 2 * 2048 : 2048;       // bytes of q / k per unit
     constexpr uint32_t UNIT_V = C == 64 ? 2 * 3072 : 3072;
-    uint32_t gu = 0;
-    TR_DECL(2);
-    auto pv = [&](int lt, int u, uint32_t g) {
-      const uint32_t b = g & 1;
-      if (u == 0) mbar_wait(bar(B_VREADY), lt & 1);
-      mbar_wait(bar(B_PREADY + b), (g >> 1) & 1);
-      tc_fence_after();
-      TR(4, lt, u);
-      if (leader) {
-        const uint32_t scol = tmem + K::SCOL0 + b * 128;
-#pragma unroll
-        for (int ks = 0; ks < C / 16; ++ks) {
-          const uint32_t b_lo = (sV + (ks >> 2) * K::V_KB + u * UNIT_V + (ks & 3) * 32) >> 4;
-          umma_ts_lo(scol + K::OOFF, scol + ks * 8, b_lo, hi, idesc_pv, ks != 0);
-        }
-        umma_commit(bar(B_OFULL + b));
-      }
-      __syncwarp();
-    };
-    for (int lt = 0; lt < T; ++lt) {
-      mbar_wait(bar(B_QKREADY), lt & 1);
-      tc_fence_after();
-      TR(1, lt, 0);
-      for (int u = 0; u < UNITS; ++u, ++gu) {
-        const uint32_t b = gu & 1;
-        if (gu >= 2) { mbar_wait(bar(B_OEMPTY + b), ((gu >> 1) - 1) & 1); tc_fence_after(); }
+    TR_DECL(warp == 2 ? 2 : 23);
+    const int total = T * UNITS;
+    if (warp == 2) {
+      for (int g = 0; g < total; ++g) {
+        const int lt = g / UNITS, u = g - lt * UNITS;
+        const int set = lt % NSET, b = g % NBUF;
+        if (g >= NBUF) mbar_wait(bar(B_OEMPTY + b), ((g / NBUF) - 1) & 1);            // unit g - NBUF drained: the buffer is free
+        if (C == 64 || !(u & 1)) mbar_wait(bar(B_QKREADY + set * 4 + (C == 64 ? u : (u >> 1))), (lt / NSET) & 1);
+        tc_fence_after();
         TR(2, lt, u);
         if (leader) {
-          const uint32_t a_lo = ((sQ + u * UNIT_Q) >> 4) | ((QK_LBO >> 4) << 16);
-          const uint32_t b_lo = ((sK + u * UNIT_Q) >> 4) | ((QK_LBO >> 4) << 16);
+          const uint32_t q0 = sSet + set * K::SET_BYTES + u * UNIT_Q;
+          const uint32_t a_lo = (q0 >> 4) | ((QK_LBO >> 4) << 16);
+          const uint32_t b_lo = ((q0 + K::QK_BYTES) >> 4) | ((QK_LBO >> 4) << 16);
           umma_bf16_lo(tmem + K::SCOL0 + b * 128, a_lo, b_lo, hi, idesc_s, false);
           umma_commit(bar(B_SFULL + b));
         }
         __syncwarp();
-        if (u >= 1) pv(lt, u - 1, gu - 1);
       }
-      pv(lt, UNITS - 1, gu - 1);
-      if (leader) umma_commit(bar(B_OPSFREE));
-      __syncwarp();
+    } else {
+      for (int g = 0; g < total; ++g) {
+        const int lt = g / UNITS, u = g - lt * UNITS;
+        const int set = lt % NSET, b = g % NBUF;
+        if (u == 0) mbar_wait(bar(B_VREADY + set), (lt / NSET) & 1);
+        mbar_wait(bar(B_PREADY + b), (g / NBUF) & 1);
+        tc_fence_after();
+        TR(4, lt, u);
+        if (leader) {
+          const uint32_t scol = tmem + K::SCOL0 + b * 128;
+          const uint32_t v0 = sSet + set * K::SET_BYTES + 2 * K::QK_BYTES + u * UNIT_V;
+#pragma unroll
+          for (int ks = 0; ks < C / 16; ++ks) {
+            const uint32_t b_lo = (v0 + (ks >> 2) * K::V_KB + (ks & 3) * 32) >> 4;
+            umma_ts_lo(scol + K::OOFF, scol + ks * 8, b_lo, hi, idesc_pv, ks != 0);
+          }
+          umma_commit(bar(B_OFULL + b));
+          // The windows of drain warp w = (C == 64 ? u : u / 2) are free once this P.V has completed: its S product finished
+          // before the softmax that produced P (so before this instruction was issued), although another warp issued it.
+          if (C == 64 || (u & 1)) umma_commit(bar(B_WINFREE + set * 4 + (C == 64 ? u : (u >> 1))));
+        }
+        __syncwarp();
+      }
     }
   } else if (warp >= 4 && warp < 8) {
     // =========================================== drain: q / k / v accumulators -> operand tiles ==========================
+    // S only needs the PRODUCT 1 / (|q_p| |k_p|) per pixel p (the contraction index), so q is stored raw and k carries both norms
+    // (and log2 e).  The sums of squares of q and k are taken as soon as the accumulators are full; the (short) write passes wait
+    // until the MMAs of the previous tile of this set have finished reading this warp's two windows.
     const int q = warp & 3;
     const int r = q * 32 + lane;               // tile row = pixel: window r >> 4, pixel-in-window r & 15
     const int w = r >> 4, px = r & 15;
@@ -352,163 +394,192 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const int sw = px & 7;
     TR_DECL(3 + q);
     for (int lt = 0; lt < T; ++lt) {
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {
-        const int slot = ch & 1;
-        const uint32_t par = slot == 0 ? (uint32_t)(ch >> 1) : (uint32_t)(lt & 1);     // slot 0: q, v alternate; slot 1: k(lt) is phase lt
-        mbar_wait(bar(B_ACCFULL + slot), par);
-        tc_fence_after();
-        TR(1, lt, ch);
-        const uint32_t tacc = tmem + slot * C + lane_addr;
-        const float* bs = sbias + ch * C;
-        if (ch < 2) {
-          float ss = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 32) {
-            float v[32];
-            tmem_ld32_sync(tacc + c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { const float t = v[j] + bs[c0 + j]; ss = fmaf(t, t, ss); }
-          }
-          // F.normalize: x / max(|x|, 1e-12); k also carries log2(e) so the softmax exponential is a bare ex2
-          const float rn = rsqrtf(fmaxf(ss, 1e-24f)) * (ch == 1 ? 1.4426950408889634f : 1.f);
-          TR(2, lt, ch);
-          if (ch == 0 && lt > 0) mbar_wait(bar(B_OPSFREE), (lt - 1) & 1);   // the previous tile's MMAs have finished reading q, k, v
-          TR(3, lt, ch);
-          uint8_t* dst0 = gen + (ch == 0 ? K::OFF_Q : K::OFF_K) + row_off;
-#pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 32) {
-            float v[32];
-            tmem_ld32_sync(tacc + c0, v);
-            if (c0 + 32 >= C) {                   // last read of this accumulator slot
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + slot));
-            }
-            uint8_t* dst = dst0 + (c0 >> 6) * (8 * 2048);
-            const int cc0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[e] = pack_bf16x2_rn((v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e]) * rn, (v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]) * rn);
-              *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-          if (ch == 1) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_QKREADY));
-          }
-          TR(4, lt, ch);
-        } else {
-          uint8_t* dst0 = gen + K::OFF_V + vrow_off;
-#pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 32) {
-            float v[32];
-            tmem_ld32_sync(tacc + c0, v);
-            if (c0 + 32 >= C) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + slot));
-            }
-            uint8_t* dst = dst0 + (c0 >> 6) * K::V_KB;
-            const int cc0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[e] = pack_f16x2_rn(v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e], v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_VREADY));
-          TR(4, lt, ch);
-        }
-      }
-    }
-  } else if (warp >= 8 && warp < 8 + 4 * NSM) {
-    // =========================================== softmax: S -> P = exp2(S) (fp16) in place =================================
-    const int q = warp & 3;
-    const int grp = (warp - 8) >> 2;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t total_units = (uint32_t)T * UNITS;
-    TR_DECL(7 + grp * 4 + q);
-    for (uint32_t gu = (NSM == 2 ? grp : 0); gu < total_units; gu += NSM) {
-      const uint32_t b = gu & 1;
-      mbar_wait(bar(B_SFULL + b), (gu >> 1) & 1);
+      const int set = lt % NSET;
+      uint8_t* set_base = gen + K::OFF_SET + set * K::SET_BYTES;
+      float ssq = 0.f, ssk = 0.f;
+      // ---- k, pass 1 (slot 1, phase lt): sum of squares only -- no smem write, so it runs ahead of the window release
+      mbar_wait(bar(B_ACCFULL + 1), lt & 1);
       tc_fence_after();
-      TR(1, gu / UNITS, gu % UNITS);
-      const uint32_t sbuf = tmem + K::SCOL0 + b * 128 + lane_addr;
-      const uint32_t scol = sbuf + (C == 64 ? 64 * (q >> 1) : 0);     // C=64: lanes 64-127 hold the pair's second window in columns 64-127
-      uint32_t pk[32];
-#pragma unroll
-      for (int kc = 0; kc < C / 32; ++kc) {
+      TR(1, lt, 1);
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
-        tmem_ld32_sync(scol + kc * 32, v);
-        TR(5, gu / UNITS, kc);
+        tmem_ld32_sync(tmem + C + lane_addr + c0, v);
+        add_bias32(v, sbias + C + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t x = pack_f16x2_rn(v[2 * j], v[2 * j + 1]);
-          pk[(kc & 1) * 16 + j] = (j & 1) ? la::exp2_poly_f16x2(x) : la::ex2_f16x2(x);
-        }
-        if (kc & 1) tmem_st32(sbuf + (kc >> 1) * 32, pk);
-        TR(6, gu / UNITS, kc);
+        for (int j = 0; j < 32; ++j) ssk = fmaf(v[j], v[j], ssk);
       }
-      tmem_st_wait();
-      TR(7, gu / UNITS, 0);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_PREADY + b));
-      TR(2, gu / UNITS, gu % UNITS);
-    }
-  } else if (warp >= 8 + 4 * NSM && warp < 12 + 4 * NSM) {
-    // =========================================== O drain + projection epilogue ==========================================
-    const int q = warp & 3;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int r = q * 32 + lane;
-    bool store_pending = false;
-    uint32_t gu = 0;
-    TR_DECL(15 + q);
-    for (int lt = 0; lt < T; ++lt) {
-      // the staging of the previous tile's TMA stores aliases the A-operand tile: drain the reads, then the whole group may write
-      if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      for (int u = 0; u < UNITS; ++u, ++gu) {
-        const uint32_t b = gu & 1;
-        mbar_wait(bar(B_OFULL + b), (gu >> 1) & 1);
-        tc_fence_after();
-        TR(1, lt, u);
-        float v[32];
-        tmem_ld32_sync(tmem + K::SCOL0 + b * 128 + K::OOFF + (C == 64 ? 24 * (q >> 1) : 0) + lane_addr, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_OEMPTY + b));
-        const float inv = __fdividef(1.f, v[16]);               // row sum of P (in [C/e^1.5, C e^1.5]) from the ones rows
-        const int win = C == 64 ? 2 * u + (q >> 1) : u;         // window of this thread's row
-        const int i = C == 64 ? 32 * (q & 1) + lane : r;        // channel of this thread's row
-        uint8_t* dst = gen + K::OFF_A + (win >> 2) * (C * 128) + i * 128;
+      TR(2, lt, 1);
+      if (lt >= NSET) mbar_wait(bar(B_WINFREE + set * 4 + q), ((lt / NSET) - 1) & 1);
+      TR(3, lt, 1);
+      // ---- q (slot 0, phase 2 lt), single pass: + bias -> sum of squares and the raw bf16 operand
+      mbar_wait(bar(B_ACCFULL + 0), 0);
+      tc_fence_after();
+      TR(1, lt, 0);
+      {
+        uint8_t* dst0 = set_base + row_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          float v[32];
+          tmem_ld32_sync(tmem + lane_addr + c0, v);
+          if (c0 + 32 >= C) {                   // last read of this accumulator slot
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + 0));
+          }
+          add_bias32(v, sbias + c0);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          uint32_t o[4];
+          for (int j = 0; j < 32; ++j) ssq = fmaf(v[j], v[j], ssq);
+          uint8_t* dst = dst0 + (c0 >> 6) * (8 * 2048);
+          const int cc0 = (c0 & 63) >> 3;
 #pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) o[k2] = pack_bf16x2_rn(v[e * 8 + 2 * k2] * inv, v[e * 8 + 2 * k2 + 1] * inv);
-          *reinterpret_cast<uint4*>(dst + (((2 * (win & 3) + e) ^ (i & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      // F.normalize: x / max(|x|, 1e-12) on each of q and k; log2(e) so the softmax exponential is a bare ex2
+      const float rn = rsqrtf(fmaxf(ssq, 1e-24f)) * rsqrtf(fmaxf(ssk, 1e-24f)) * 1.4426950408889634f;
+      // ---- k, pass 2: (k + bias) / (|q_p| |k_p|) * log2 e
+      {
+        uint8_t* dst0 = set_base + K::QK_BYTES + row_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          float v[32];
+          tmem_ld32_sync(tmem + C + lane_addr + c0, v);
+          if (c0 + 32 >= C) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + 1));
+          }
+          add_bias32(v, sbias + C + c0);
+          uint8_t* dst = dst0 + (c0 >> 6) * (8 * 2048);
+          const int cc0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_rn(v[g * 8 + 2 * e] * rn, v[g * 8 + 2 * e + 1] * rn);
+            *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_ASREADY));
-      TR(2, lt, 0);
-      // ---- projection accumulators of this tile (slot 1): + bias -> bf16 -> swizzled staging -> TMA store
+      if (lane == 0) mbar_arrive(bar(B_QKREADY + set * 4 + q));
+      TR(4, lt, 1);
+      // ---- v (slot 0, phase 2 lt + 1): + bias -> fp16
+      mbar_wait(bar(B_ACCFULL + 0), 1);
+      tc_fence_after();
+      TR(1, lt, 2);
+      {
+        uint8_t* dst0 = set_base + 2 * K::QK_BYTES + vrow_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          float v[32];
+          tmem_ld32_sync(tmem + lane_addr + c0, v);
+          if (c0 + 32 >= C) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_ACCEMPTY + 0));
+          }
+          add_bias32(v, sbias + 2 * C + c0);
+          uint8_t* dst = dst0 + (c0 >> 6) * K::V_KB;
+          const int cc0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = pack_f16x2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_VREADY + set));
+      TR(4, lt, 2);
+    }
+  } else if (warp >= 8 && warp < EP0) {
+    // =========================================== softmax + O drain: one group of four warps per S buffer ==================
+    // group b owns buffer b (units b, b + NBUF, ...): S -> P = exp2(S) (fp16, in place) -> [issuer A: P.V] -> O / rowsum -> bf16
+    // -> the projection's MN-major A tile.  The NBUF lifecycles run staggered, so the tensor pipe always has a unit to work on.
+    const int q = warp & 3;
+    const int grp = (warp - 8) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int total = T * UNITS;
+    const uint32_t sbuf = tmem + K::SCOL0 + grp * 128 + lane_addr;
+    const uint32_t scol = sbuf + (C == 64 ? 64 * (q >> 1) : 0);       // C=64: lanes 64-127 hold the pair's second window in columns 64-127
+    const uint32_t ocol = sbuf + K::OOFF + (C == 64 ? 24 * (q >> 1) : 0);
+    const int i_ch = C == 64 ? 32 * (q & 1) + lane : q * 32 + lane;   // channel of this thread's row
+    TR_DECL(7 + grp * 4 + q);
+    uint32_t ph = 0;
+    for (int g = grp; g < total; g += NBUF, ph ^= 1u) {
+      const int lt = g / UNITS, u = g - lt * UNITS;
+      mbar_wait(bar(B_SFULL + grp), ph);
+      tc_fence_after();
+      TR(1, lt, u);
+#pragma unroll
+      for (int kc = 0; kc < C / 32; ++kc) {
+        float v[32];
+        tmem_ld32_sync(scol + kc * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t x = pack_f16x2_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = (j & 1) ? la::exp2_poly_f16x2(x) : la::ex2_f16x2(x);
+        }
+        tmem_st16(sbuf + kc * 16, pk);          // P columns [16 kc, 16 kc + 16) <- S columns [32 kc, 32 kc + 32), already consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PREADY + grp));
+      TR(2, lt, u);
+      // ---- O of the same unit
+      mbar_wait(bar(B_OFULL + grp), ph);
+      tc_fence_after();
+      TR(3, lt, u);
+      float v[32];
+      tmem_ld32_sync(ocol, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_OEMPTY + grp));
+      // first unit of this group in tile lt: the projection of tile lt - 1 must have finished reading the A tile
+      if (g - NBUF < lt * UNITS && lt >= 1) mbar_wait(bar(B_PFULL), (lt - 1) & 1);
+      const float inv = __fdividef(1.f, v[16]);               // row sum of P (in [C/e^1.5, C e^1.5]) from the ones rows
+      const int win = C == 64 ? 2 * u + (q >> 1) : u;         // window of this thread's row
+      uint8_t* dst = gen + K::OFF_A + (win >> 2) * (C * 128) + i_ch * 128;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) o[k2] = pack_bf16x2_rn(v[e * 8 + 2 * k2] * inv, v[e * 8 + 2 * k2 + 1] * inv);
+        *reinterpret_cast<uint4*>(dst + (((2 * (win & 3) + e) ^ (i_ch & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      if (g + NBUF >= (lt + 1) * UNITS) {       // last unit of this group in the tile
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_ASREADY));
+      }
+      TR(4, lt, u);
+    }
+  } else if (warp >= EP0 && warp < EP0 + 4) {
+    // =========================================== projection epilogue ====================================================
+    // staging at C=128 = the x stage, whose tile (lt + 1) the qkv GEMMs have consumed: PFULL(lt) is committed by issuer G after
+    // those GEMMs, so its completion implies they are done; the producer reloads the stage only after STFREE
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane;
+    const float* bs = sbias + 3 * C;
+    TR_DECL(19 + q);
+    for (int lt = 0; lt < T; ++lt) {
       mbar_wait(bar(B_PFULL), lt & 1);
       tc_fence_after();
       TR(3, lt, 0);
-      const float* bs = sbias + 3 * C;
 #pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
@@ -518,14 +589,14 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(B_PEMPTY));
         }
-        uint8_t* dst = gen + K::OFF_A + (c0 >> 6) * K::X_TILE + r * 128;
+        add_bias32(v, bs + c0);
+        uint8_t* dst = gen + K::OFF_STG + (c0 >> 6) * K::X_TILE + r * 128;
         const int cc0 = (c0 & 63) >> 3;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[e] = pack_bf16x2_rn(v[g * 8 + 2 * e] + bs[c0 + g * 8 + 2 * e], v[g * 8 + 2 * e + 1] + bs[c0 + g * 8 + 2 * e + 1]);
+          for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
           *reinterpret_cast<uint4*>(dst + (((cc0 + g) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
@@ -535,16 +606,18 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         int img, h0, wc0;
         tile_coords(t_begin + lt, img, h0, wc0);
         for (int kb = 0; kb < KB; ++kb)
-          tma_store_5d(&mapOut, sA + kb * K::X_TILE + q * 4096, kb * 64, 0, h0, wc0 + 2 * q, img);
+          tma_store_5d(&mapOut, base + K::OFF_STG + kb * K::X_TILE + q * 4096, kb * 64, 0, h0, wc0 + 2 * q, img);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        store_pending = true;
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(bar(B_STFREE));
       }
+      __syncwarp();
       TR(4, lt, 0);
     }
-    if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  } else if (XF && warp >= 12 + 4 * NSM) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (XF && warp >= XF0) {
     // =========================================== fused input InstanceNorm + activation (as conv_tma.cu) ===================
-    const int xt = tid - 32 * (12 + 4 * NSM);          // 0..127
+    const int xt = tid - 32 * XF0;         // 0..127
     const int pchunk = xt & 7, rbase = xt >> 3;
     const int lchunk = pchunk ^ (rbase & 7);
     const double inv_hw = 1.0 / ((double)p.H * (double)p.W);
@@ -565,8 +638,8 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         asm volatile("bar.sync 2, 128;" ::: "memory");
         cur_img = img;
       }
-      const int xs = lt % K::XS;
-      mbar_wait(bar(B_XFULL + xs), (lt / K::XS) & 1);
+      const int xs = lt % XS;
+      mbar_wait(bar(B_XFULL + xs), (lt / XS) & 1);
 #pragma unroll 1
       for (int kb = 0; kb < KB; ++kb) {
         float sc[8], sh[8];
@@ -604,17 +677,17 @@ la_stage_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
 unsigned long long* g_trace = nullptr;
 
-template <int C, int NSM, bool XF>
+template <int C, bool XF>
 int launch(const CUtensorMap& mX, const CUtensorMap& mQ, const CUtensorMap& mP, const CUtensorMap& mO, const LaParams& p, cudaStream_t st) {
   static DeviceOnce attr_set;
   if (attr_set.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(la_stage_kernel<C, NSM, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(la_stage_kernel<C, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM);
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "la_stage: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set.done();
   }
   int grid = sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  la_stage_kernel<C, NSM, XF><<<grid, 32 * (12 + 4 * NSM + (XF ? 4 : 0)), Cfg<C>::SMEM, st>>>(mX, mQ, mP, mO, p);
+  la_stage_kernel<C, XF><<<grid, 32 * (12 + 4 * Cfg<C>::NBUF + (XF ? 4 : 0)), Cfg<C>::SMEM, st>>>(mX, mQ, mP, mO, p);
   return check_launch("la_stage_kernel");
 }
 
@@ -664,23 +737,16 @@ int la_stage_fwd(const void* x, const double* in_stats, int in_act, const void* 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "la_stage: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
   }
-  const char* env = getenv("MSG_LA_SOFTMAX_GROUPS");      // (read per call: the tests switch it)
-  const int env_nsm = env ? atoi(env) : 0;
   const bool xf = in_stats != nullptr;
-  const int nsm = env_nsm == 1 || env_nsm == 2 ? env_nsm : 2;
-  if (C == 64) {
-    if (nsm == 2) return xf ? launch<64, 2, true>(mX, mQ, mP, mO, p, st) : launch<64, 2, false>(mX, mQ, mP, mO, p, st);
-    return xf ? launch<64, 1, true>(mX, mQ, mP, mO, p, st) : launch<64, 1, false>(mX, mQ, mP, mO, p, st);
-  }
-  if (nsm == 2) return xf ? launch<128, 2, true>(mX, mQ, mP, mO, p, st) : launch<128, 2, false>(mX, mQ, mP, mO, p, st);
-  return xf ? launch<128, 1, true>(mX, mQ, mP, mO, p, st) : launch<128, 1, false>(mX, mQ, mP, mO, p, st);
+  if (C == 64) return xf ? launch<64, true>(mX, mQ, mP, mO, p, st) : launch<64, false>(mX, mQ, mP, mO, p, st);
+  return xf ? launch<128, true>(mX, mQ, mP, mO, p, st) : launch<128, false>(mX, mQ, mP, mO, p, st);
 }
 
 }  // namespace msg
 
 using namespace msg;
 
-/* development hook (MSG_LA_TRACE builds): device buffer of 19 x 4096 u64 receiving CTA 0's role timelines; NULL = off */
+/* development hook (MSG_LA_TRACE builds): device buffer of 24 x 4096 u64 receiving CTA 0's role timelines; NULL = off */
 extern "C" int msg_la_stage_set_trace(void* buf) {
   g_trace = reinterpret_cast<unsigned long long*>(buf);
   return MSG_OK;

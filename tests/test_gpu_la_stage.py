@@ -25,9 +25,9 @@ def _bf(t):
 
 
 @pytest.mark.parametrize("C,N,H,W", [(64, 1, 4, 32), (64, 2, 8, 64), (128, 1, 4, 32), (128, 2, 16, 32),
-                                       (64, 3, 12, 40), (128, 2, 8, 8), (64, 1, 64, 96), (128, 1, 32, 160)])
-@pytest.mark.parametrize("groups", ["1", "2"])
-def test_la_stage_matches_oracle(C, N, H, W, groups, monkeypatch):
+                                       (64, 3, 12, 40), (128, 2, 8, 8), (64, 1, 64, 96), (128, 1, 32, 160),
+                                       (64, 4, 128, 128), (128, 4, 64, 128)])
+def test_la_stage_matches_oracle(C, N, H, W):
     from multi_style_transfer_gan_b200 import ops
     from oracle import restate as R
     x, wq, bq, wp, bp = _case(C, N, H, W, seed=C + H + W)
@@ -37,8 +37,6 @@ def test_la_stage_matches_oracle(C, N, H, W, groups, monkeypatch):
     wqd = ops.pack_weight(wq.to(DEV), ops.PACK_FWD, torch.bfloat16)
     wpd = ops.pack_weight(wp.to(DEV), ops.PACK_FWD, torch.bfloat16)
     assert ops.la_stage_supported(xd, wqd, wpd)
-    import os
-    os.environ["MSG_LA_SOFTMAX_GROUPS"] = groups      # read once per process by the library: only the first value is effective
     out = ops.la_stage_fwd(xd, wqd, bq.to(DEV), wpd, bp.to(DEV))
     torch.cuda.synchronize()
     assert_parity(out.float().permute(0, 3, 1, 2).cpu(), ref, 2e-2, f"la_stage C={C} {H}x{W}")

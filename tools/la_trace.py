@@ -11,13 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multi_style_transfer_gan_b200 import _lib, ops  # noqa: E402
 
 ROLES = ["producer", "issuerG", "issuerA", "drain0", "drain1", "drain2", "drain3", "sm0.0", "sm0.1", "sm0.2", "sm0.3",
-         "sm1.0", "sm1.1", "sm1.2", "sm1.3", "epi0", "epi1", "epi2", "epi3"]
+         "sm1.0", "sm1.1", "sm1.2", "sm1.3", "sm2.0", "sm2.1", "sm2.2", "sm2.3", "epi0", "epi1", "epi2", "epi3", "issuerPV"]
 EV = {"producer": {1: "x load issue"},
       "issuerG": {1: "x ready", 2: "chunk slot free", 3: "chunk issued", 10: "proj start", 11: "proj issued"},
       "issuerA": {1: "qk ready", 2: "S buf free -> issue S", 4: "P ready -> issue PV"},
-      "drain": {1: "acc full", 2: "pass1 done", 3: "ops free", 4: "chunk stored"},
-      "sm": {1: "S full", 2: "P stored", 5: "ld done", 6: "chunk computed", 7: "st waited"},
-      "epi": {1: "O full", 2: "As ready", 3: "proj full", 4: "store issued"}}
+      "issuerPV": {4: "P ready -> issue PV"},
+      "drain": {1: "acc full", 2: "pass1 done", 3: "windows free", 4: "chunk stored"},
+      "sm": {1: "S full", 2: "P stored", 3: "O full", 4: "O drained"},
+      "epi": {3: "proj full", 4: "store done"}}
 
 
 def main():
@@ -32,12 +33,12 @@ def main():
     st = ops.instnorm_stats(x)
     for _ in range(2):
         ops.la_stage_fwd(x, wq, bq, wp, bp, in_stats=st, in_act=ops.ACT_RELU)
-    buf = torch.zeros(19 * 4096, device="cuda", dtype=torch.int64)
+    buf = torch.zeros(24 * 4096, device="cuda", dtype=torch.int64)
     _lib.load().msg_la_stage_set_trace(ctypes.c_void_p(buf.data_ptr()))
     ops.la_stage_fwd(x, wq, bq, wp, bp, in_stats=st, in_act=ops.ACT_RELU)
     torch.cuda.synchronize()
     _lib.load().msg_la_stage_set_trace(None)
-    b = buf.cpu().view(19, 4096)
+    b = buf.cpu().view(24, 4096)
     evs = []
     for r, name in enumerate(ROLES):
         n = int(b[r, 4094])
@@ -53,11 +54,11 @@ def main():
     t0 = min(c for c, n, e, lt, u in evs if lt == tile)
     per_tile = {}
     for c, n, e, lt, u in evs:
-        if n == "issuerA" and e == "qk ready":
+        if n == "issuerA" and e == "S buf free -> issue S" and u == 0:
             per_tile[lt] = c
     ks = sorted(per_tile)
     print("tiles of CTA 0:", len(ks), " cycles between 'qk ready' of consecutive tiles:", [per_tile[b_] - per_tile[a] for a, b_ in zip(ks, ks[1:])][:12])
-    only = {"producer", "issuerG", "issuerA", "drain0", "sm0.0", "sm1.0", "epi0"}
+    only = {"producer", "issuerG", "issuerA", "issuerPV", "drain0", "drain3", "sm0.0", "sm1.0", "sm2.0", "epi0"}
     for c, n, e, lt, u in evs:
         if lt in (tile, tile + 1) and n in only:
             print(f"{c - t0:8d}  {n:9s} tile {lt} unit {u}  {e}")
