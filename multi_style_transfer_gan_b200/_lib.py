@@ -8,7 +8,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsg_b200.so")
+LIB_PATH = os.environ.get("MSG_B200_LIB") or os.path.join(HERE, "libmsg_b200.so")   # (env: development A/B builds)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3

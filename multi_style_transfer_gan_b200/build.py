@@ -21,6 +21,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 if os.environ.get("MSG_LA_TRACE") == "1":      # development build: role timelines of the fused LocalAttention kernel (tools/la_trace.py)
     FLAGS.append("-DMSG_LA_TRACE")
+# development A/B builds: MSG_NVCC_DEFS="-DX=1 -DY" MSG_LIB_SUFFIX=_x python -m multi_style_transfer_gan_b200.build writes
+# libmsg_b200_x.so beside the product library; MSG_B200_LIB=<path> makes _lib.py open it instead
+FLAGS += os.environ.get("MSG_NVCC_DEFS", "").split()
+_SUFFIX = os.environ.get("MSG_LIB_SUFFIX", "")
+if _SUFFIX:
+    OBJ = os.path.join(HERE, "build" + _SUFFIX)
+    LIB = os.path.join(HERE, f"libmsg_b200{_SUFFIX}.so")
 
 
 def _digest(paths):

@@ -159,7 +159,9 @@ conv_simt_kernel(const msg_conv_desc d, const T* __restrict__ x, const T* __rest
     const int hw = d.Hg * d.Wg;
     long long mlast = m0 + BM - 1 < M ? m0 + BM - 1 : M - 1;
     int n_first = (int)(m0 / hw), n_last = (int)(mlast / hw);
-    if (n_first == n_last) {
+    // fp32 tile partials only when tiles never straddle images (plane a multiple of the tile): otherwise the grouping of an
+    // image's rows would depend on its position in the batch, and with it the last bits of its statistics
+    if (n_first == n_last && hw % BM == 0) {
       float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

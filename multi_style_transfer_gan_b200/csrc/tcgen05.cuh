@@ -18,14 +18,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: without one a waiting warp comes back every ~30 cycles and the BRA / TRYWAIT / YIELD
+// of its retry loop were 56 % of the instructions the fused LocalAttention kernel executed (ncu source page) -- issue slots
+// taken from the warps doing the work.  With the hint the hardware parks the warp until the phase completes or the time is up.
+#ifndef MSG_MBAR_SUSPEND_HINT
+#define MSG_MBAR_SUSPEND_HINT 0x989680u
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(MSG_MBAR_SUSPEND_HINT) : "memory");
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
