@@ -484,7 +484,7 @@ extern "C" int msg_conv2d_wgrad(const msg_conv_desc* d, const void* x, const voi
   int rc = validate_desc(d);
   if (rc) return rc;
   MSG_REQUIRE(!(d->flags & MSG_CONV_OUT_NCHW_F32), MSG_ERR_UNSUPPORTED, "wgrad: NCHW dy unsupported");
-  if (!(d->flags & MSG_CONV_FORCE_SIMT) && conv2d_wgrad_tc_supported(d, x, dy))
+  if (!(d->flags & MSG_CONV_FORCE_SIMT) && !((uintptr_t)dw_packed & 15) && conv2d_wgrad_tc_supported(d, x, dy))   // (bulk reduce: 16-byte rows)
     return conv2d_wgrad_tc(d, x, dy, dw_packed, as_stream(stream));      // tcgen05 kernel (conv_wgrad_tc.cu)
   const int K = d->KH * d->KW * d->Cin;
   const long long M = (long long)d->N * d->Hg * d->Wg;

@@ -151,27 +151,42 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     __syncwarp();
     if (elect_one()) umma_commit(done_bar);
   } else {
-    // ===================================== epilogue: TMEM -> fp32 atomics on dw =====================
+    // ===================================== epilogue: TMEM -> shared memory -> bulk reduce-add on dw =====================
+    // A thread owns one co row.  The row's npair x 64 fp32 values are staged in the (now idle) pipeline memory and added to dw
+    // with ONE cp.reduce.async.bulk (256 contiguous bytes) per (row, pair): the scalar atomicAdd version issued 64 atomics per
+    // thread and pair, each warp instruction touching 32 different rows -- the fixed ~50 us that made every weight-gradient
+    // launch of the train step cost the same whatever its size.
     const int q = warp & 3;
-    const int co = cot * 128 + q * 32 + lane;
+    const int row = q * 32 + lane;
+    const int co = cot * 128 + row;
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int Ktot = d.KH * d.KW * d.Cin;
     if (mt_end > mt_begin) {
+      const int pitch = npair * 256 + 16;                        // bytes; + 16: conflict-free 16-byte stores down a column of rows
+      uint8_t* srow = gen + (size_t)row * pitch;
       for (int pi = 0; pi < npair; ++pi) {
-        const int pr = pair0 + pi;
-        const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
-        float* dst = p.dw + (size_t)out_img * d.Cout * Ktot + (size_t)co * Ktot + (size_t)tap * d.Cin + cb * 64;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           __syncwarp();
           float v[32];
           tmem_ld32_sync(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + h * 32), v);
-          if (co < d.Cout) {
+          float4* o = reinterpret_cast<float4*>(srow + pi * 256 + h * 128);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + h * 32 + j, v[j]);
-          }
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+      }
+      fence_proxy_async();
+      if (co < d.Cout) {
+        for (int pi = 0; pi < npair; ++pi) {
+          const int pr = pair0 + pi;
+          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
+          float* dst = p.dw + (size_t)out_img * d.Cout * Ktot + (size_t)co * Ktot + (size_t)tap * d.Cin + cb * 64;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 256;"
+                       ::"l"(dst), "r"(base + (uint32_t)(row * pitch + pi * 256)) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging must outlive the reads
       }
     }
   }
@@ -232,7 +247,7 @@ int conv2d_wgrad_tc_impl(const msg_conv_desc* d, const void* x, const void* dy, 
   p.groups = (p.n_pairs + MAXP - 1) / MAXP;
   p.co_tiles = (d->Cout + 127) / 128;
   const int items = p.groups * p.co_tiles;
-  int splits = (2 * sm_count() + items - 1) / items;     // ~2 CTAs' worth of work items per SM in total
+  int splits = sm_count() / items;                       // ONE wave of CTAs (one CTA per SM: 192 KB of pipeline stages each)
   if (splits > p.m_tiles) splits = p.m_tiles;
   if (splits < 1) splits = 1;
   p.per_image = per_image ? 1 : 0;
@@ -240,7 +255,7 @@ int conv2d_wgrad_tc_impl(const msg_conv_desc* d, const void* x, const void* dy, 
   if (per_image) {
     MSG_REQUIRE(p.m_tiles % d->N == 0, MSG_ERR_SHAPE, "wgrad_tc: per-image mode needs whole tiles per image");
     const int tpi = p.m_tiles / d->N;
-    int spi = (2 * sm_count() + items * d->N - 1) / (items * d->N);
+    int spi = sm_count() / (items * d->N);
     if (spi > tpi) spi = tpi;
     if (spi < 1) spi = 1;
     p.splits_per_image = spi;
