@@ -316,17 +316,28 @@ def bench_train(cx, args, steps, warmup):
     if args.lambda_style > 0:                  # + VGG-19 Gram style term (random-init trunk, seed 0)
         from multi_style_transfer_gan_b200.style_loss import GramStyleLoss, VGG19Features
         style = GramStyleLoss(VGG19Features(cx.dev, seed=0), precision=args.precision)
+    use_graph = not args.no_train_graph
     m = EnhancedCycleGAN(channels=c, num_transformer_blocks=3 if c == 64 else 1, precision=args.precision, device=cx.dev,
-                         style_loss=style, lambda_style=args.lambda_style)
+                         style_loss=style, lambda_style=args.lambda_style, use_graph=use_graph, graph_warmup=2)
     B, S = args.train_batch, args.train_size
     A = synth_images(B, S, S, seed=11 + cx.rank).pin_memory()
     Bm = synth_images(B, S, S, seed=12 + cx.rank).pin_memory()
-    for _ in range(warmup):
+    # eager steps first (with use_graph: the two steps before the capture): the NCCL all-reduce is timed here, bracketed by CUDA
+    # events on the launching stream -- launches inside a replayed graph cannot be bracketed
+    m.comm_log = []
+    n_eager = 2
+    for _ in range(n_eager):
+        m.train_step(A, Bm)
+    torch.cuda.synchronize()
+    comm_ms = sum(a.elapsed_time(b) for a, b, _ in m.comm_log) / n_eager
+    comm_bytes = sum(n for _, _, n in m.comm_log) // n_eager
+    comm_calls = len(m.comm_log) // n_eager
+    comm_ms = cx.max_over_ranks(comm_ms)
+    m.comm_log = None
+    for _ in range(max(0, warmup - n_eager) + (1 if use_graph else 0)):      # (+ the capturing step)
         m.train_step(A, Bm)
     cx.barrier()
-    m.comm_log = []
     l0 = _lib.launches
-    profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -334,30 +345,38 @@ def bench_train(cx, args, steps, warmup):
     e1.record()
     cx.barrier()
     ms = cx.max_over_ranks(e0.elapsed_time(e1) / steps)
+    launches_per_step = (_lib.launches - l0) // steps
+    graphed = m._graph is not None
+    # per-entry-point breakdown: one more step run eagerly (same kernels; a replayed graph cannot be bracketed by events)
+    m.use_graph = False
+    profiler.start()
+    m.train_step(A, Bm)
     breakdown = profiler.stop()
-    comm_ms = sum(a.elapsed_time(b) for a, b, _ in m.comm_log) / steps
-    comm_bytes = sum(n for _, _, n in m.comm_log) // max(1, steps)
-    comm_ms = cx.max_over_ranks(comm_ms)
+    bsteps = 1
     pk = peaks()
-    wg_ms = breakdown.get("msg_conv2d_wgrad", {}).get("ms", 0.0) / steps
+    wg_ms = breakdown.get("msg_conv2d_wgrad", {}).get("ms", 0.0) / bsteps
     out = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
            "scaling": "weak", "dtype": "bf16" if args.precision == "bf16" else "f32",
            "config": {"workload": "EnhancedCycleGAN.train_step (2 G + 2 D, LSGAN + cycle + identity + structure losses"
                                   + (f" + {args.lambda_style:g} x VGG-19 Gram style loss (random-init trunk)" if style else "")
                                   + f", fused Adam), c={c}, batch {B} per GPU at {S}x{S}",
-                      "global_batch": B * cx.world, "parallelism": f"data-parallel x{cx.world}, 2 flat NCCL all-reduces per step"},
+                      "global_batch": B * cx.world, "parallelism": f"data-parallel x{cx.world}, 2 flat NCCL all-reduces per step",
+                      "schedule": "whole step replayed as one CUDA graph" if graphed else
+                                  ("eager launches" + (f" (graph capture failed: {m.graph_error})" if m.graph_error else ""))},
            "images_per_sec": B * cx.world * 1e3 / ms,
-           "gpu_launches_per_step": (_lib.launches - l0) // steps, "losses": losses,
-           "nccl": {"ms_per_step": comm_ms, "bytes_per_step": comm_bytes, "calls_per_step": len(m.comm_log) // max(1, steps),
-                    "how": "CUDA events around dist.all_reduce on the launching stream, max over ranks"},
+           "gpu_launches_per_step": launches_per_step, "losses": losses,
+           "nccl": {"ms_per_step": comm_ms, "bytes_per_step": comm_bytes, "calls_per_step": comm_calls,
+                    "how": "CUDA events around dist.all_reduce on the launching stream, max over ranks, on the eager steps before the "
+                           "graph capture"},
            "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": 2 * A.numel() * 4, "d2h_bytes_per_step": 20},
-           "breakdown_ms_per_step": {k: round(v["ms"] / steps, 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
+           "breakdown_ms_per_step": {k: round(v["ms"] / bsteps, 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:12]},
+           "breakdown_note": "one eager step after the timed region (same kernels)"}
     if wg_ms > 0 and c == 64 and S == 256:
         ach = TRAIN_WGRAD_GFLOP_PER_IMAGE * B * 1e9 / (wg_ms * 1e-3) / 1e12
         out["roofline_wgrad"] = {"bound": "tensor", "kernel": "conv_wgrad_tc_kernel (every weight-gradient launch of the step)",
                                  "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                  "frac": ach / pk["bf16_tflops_sustained"], "ms_per_step": wg_ms,
-                                 "launches_per_step": breakdown["msg_conv2d_wgrad"]["launches"] // steps}
+                                 "launches_per_step": breakdown["msg_conv2d_wgrad"]["launches"] // bsteps}
     del m
     torch.cuda.empty_cache()
     return out
@@ -561,6 +580,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the embedded train / gram / highres measurements")
     ap.add_argument("--workload", default="stylise", choices=["stylise", "train"])
+    ap.add_argument("--no-train-graph", action="store_true", help="train workload: eager launches instead of one CUDA-graph replay per step")
     ap.add_argument("--train-batch", type=int, default=8)
     ap.add_argument("--train-size", type=int, default=256)
     ap.add_argument("--lambda-style", type=float, default=0.0,

@@ -283,6 +283,11 @@ int msg_l1_loss(const float* a, const float* b, float b_const, long long n, floa
 int msg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* as msg_adam_step with the step count kept in device memory: *step_dev is incremented, then used for the bias corrections
+ * (host double-precision pow of msg_adam_step restated on the device).  For CUDA-graph replays of a whole train step. */
+int msg_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                      float beta2, float eps, int* step_dev, float grad_scale, void* stream);
+
 /* spectral norm (old-style torch.nn.utils.spectral_norm, enhanced_generator.py:269-271):
  * one power iteration on W[rows][cols] (fp32), updating u[rows], v[cols] in place, then
  * sigma = u^T W v written to *sigma.  do_power_iter=0 (eval) only computes sigma. */

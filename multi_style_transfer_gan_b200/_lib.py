@@ -85,6 +85,7 @@ SIGNATURES = {
     "msg_mse_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P],
     "msg_l1_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],
+    "msg_adam_step_dev": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, c_float, _P],
     "msg_spectral_norm": [_P, c_int, c_int, _P, _P, c_int, c_float, _P, _P],
     "msg_spectral_norm_bwd": [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "msg_gram": [c_int, _P, c_int, c_ll, c_int, _P, _P],

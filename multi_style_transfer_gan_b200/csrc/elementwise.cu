@@ -411,6 +411,36 @@ extern "C" int msg_l1_loss(const float* a, const float* b, float b_const, long l
   return check_launch("l1_kernel");
 }
 
+// as adam_kernel with the step count read from device memory (a captured CUDA graph replays the same launch every step, so
+// the bias corrections cannot be launch arguments); *step is incremented by adam_step_incr_kernel in front of it
+__global__ void adam_step_incr_kernel(int* step) { *step += 1; }
+__global__ void __launch_bounds__(EW_TPB)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                const int* __restrict__ step, float gscale) {
+  const int t = *step;
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)t));
+  const float sqrt_bc2 = (float)sqrt(1.0 - pow((double)b2, (double)t));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+extern "C" int msg_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                 float beta1, float beta2, float eps, int* step_dev, float grad_scale,
+                                 void* stream) {
+  MSG_REQUIRE(n > 0 && step_dev != nullptr, MSG_ERR_SHAPE, "adam: bad arguments");
+  adam_step_incr_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+  adam_dev_kernel<<<ew_blocks(n, 2), EW_TPB, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale);
+  return check_launch("adam_dev_kernel");
+}
+
 extern "C" int msg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
                              float beta1, float beta2, float eps, int step, float grad_scale,
                              void* stream) {

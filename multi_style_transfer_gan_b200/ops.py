@@ -427,6 +427,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
               float(eps), int(step), float(grad_scale), _stream())
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    """as adam_step with the step count in device memory (int32 tensor, incremented by the call): graph-replayable"""
+    _lib.call("msg_adam_step_dev", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+              float(eps), _p(step_dev), float(grad_scale), _stream())
+
+
 def spectral_norm(w2d_like, rows, cols, u, v, do_iter, sigma, eps=1e-12):
     _lib.call("msg_spectral_norm", _p(w2d_like), rows, cols, _p(u), _p(v), int(do_iter), float(eps), _p(sigma), _stream())
 
