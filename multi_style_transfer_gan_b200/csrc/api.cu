@@ -52,6 +52,9 @@ bool conv2d_tc_supported(const msg_conv_desc* d, const void* x, const void* w, c
 int conv2d_tc(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
               double* stats, const double* in_stats, cudaStream_t st);
 
+bool conv2d_dot_supported(const msg_conv_desc* d, const void* x, const void* w);
+int conv2d_dot(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, cudaStream_t st);
+
 int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     double* stats, const double* in_stats, cudaStream_t st) {
   int rc = conv_validate(d);
@@ -59,6 +62,8 @@ int conv2d_dispatch(const msg_conv_desc* d, const void* x, const void* w, const 
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_STATS without a stats buffer");
   MSG_REQUIRE(!(d->flags & MSG_CONV_IN_NORM) || in_stats != nullptr, MSG_ERR_SHAPE, "conv: MSG_CONV_IN_NORM without in_stats");
   if (!(d->flags & MSG_CONV_FORCE_SIMT)) {
+    if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_dot_supported(d, x, w))
+      return conv2d_dot(d, x, w, bias, y, st);                              // one useful GEMM column: warp-per-pixel dot products
     if (!(d->flags & MSG_CONV_FORCE_GATHER) && conv2d_tma_supported(d, x, w, y))
       return conv2d_tma(d, x, w, bias, y, stats, in_stats, st);            // persistent TMA + tcgen05 kernel
     MSG_REQUIRE(!(d->flags & MSG_CONV_PER_IMAGE_W), MSG_ERR_UNSUPPORTED,

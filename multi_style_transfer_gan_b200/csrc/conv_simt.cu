@@ -451,6 +451,76 @@ int validate_desc(const msg_conv_desc* d) {
 
 }  // namespace
 
+// ---- Cout <= 2, long K (the discriminator heads: 4x4 conv 512 -> 1 on a 15x15 map, enhanced_generator.py:256,265): a GEMM
+// with one useful column.  On the tensor-core gather kernel it is 15 CTAs each walking 128 K blocks in sequence (0.13 ms for
+// 29 MFLOP, 20 launches per train step); here one WARP owns an output pixel, its lanes stride over the 16-byte chunks of the
+// (tap, channel) axis, and a shuffle tree finishes the dot product.
+template <int CO>
+__global__ void __launch_bounds__(256)
+conv_dot_kernel(const msg_conv_desc d, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long M = (long long)d.N * d.Hg * d.Wg;
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int n = (int)(m / (d.Hg * d.Wg));
+  const int rem = (int)(m - (long long)n * d.Hg * d.Wg);
+  const int i = rem / d.Wg, j = rem - i * d.Wg;
+  const int c8 = d.Cin >> 3, chunks = d.KH * d.KW * c8;
+  const int K = d.KH * d.KW * d.Cin;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int ch = lane; ch < chunks; ch += 32) {
+    const int tap = ch / c8, cc = ch - tap * c8;
+    const int th = tap / d.KW, tw = tap - th * d.KW;
+    const int ih = i * d.in_stride - d.pad_h + th * d.dil, iw = j * d.in_stride - d.pad_w + tw * d.dil;
+    if (ih < 0 || ih >= d.Hi || iw < 0 || iw >= d.Wi) continue;
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + (((size_t)n * d.Hi + ih) * d.Wi + iw) * d.Ci_total + d.ci_off + cc * 8);
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(w + (size_t)c * K + (size_t)tap * d.Cin + cc * 8);
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[c] = fmaf(__uint_as_float(xw[e] << 16), __uint_as_float(ww[e] << 16), acc[c]);
+        acc[c] = fmaf(__uint_as_float(xw[e] & 0xffff0000u), __uint_as_float(ww[e] & 0xffff0000u), acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+  }
+  if (lane == 0) {
+    const int oh = i * d.out_stride + d.out_off_h, ow = j * d.out_stride + d.out_off_w;
+    __nv_bfloat16* dst = y + (((size_t)n * d.Ho + oh) * d.Wo + ow) * d.Co_total + d.co_off;
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+      if (c < d.Cout) dst[c] = __float2bfloat16_rn(apply_act(acc[c] + (bias ? bias[c] : 0.f), d.act));
+  }
+}
+
+bool conv2d_dot_supported(const msg_conv_desc* d, const void* x, const void* w) {
+  if (d->dtype != MSG_BF16 || d->Cout > 2) return false;
+  if (d->flags & (MSG_CONV_STATS | MSG_CONV_OUT_NCHW_F32 | MSG_CONV_ACCUM | MSG_CONV_PER_IMAGE_W | MSG_CONV_IN_NORM)) return false;
+  if ((d->Cin | d->Ci_total | d->ci_off) & 7) return false;
+  if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
+  return d->KH * d->KW * d->Cin >= 2048;
+}
+
+int conv2d_dot(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, cudaStream_t st) {
+  const long long M = (long long)d->N * d->Hg * d->Wg;
+  const unsigned grid = (unsigned)((M + 7) / 8);
+  if (d->Cout == 1)
+    conv_dot_kernel<1><<<grid, 256, 0, st>>>(*d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y);
+  else
+    conv_dot_kernel<2><<<grid, 256, 0, st>>>(*d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y);
+  return check_launch("conv_dot_kernel");
+}
+
 int conv2d_simt(const msg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                 double* stats, const double* in_stats, cudaStream_t st) {
   const long long M = (long long)d->N * d->Hg * d->Wg;

@@ -100,7 +100,8 @@ class DiscriminatorEngine:
                 m = self._master(w_orig, n, dtype)
                 dw = torch.zeros_like(m)
                 db = torch.zeros(geom.Cout, device=m.device, dtype=torch.float32)
-                geom.wgrad(x, dy, dw, db)
+                # (biases of the convs in front of an InstanceNorm: exactly zero gradient, see generator_engine._conv_bwd)
+                geom.wgrad(x, dy, dw, None if n in ("main.2", "main.5", "main.8", "structure_head.0") else db)
                 if n == "main.0":
                     dw = dw[:, :3].contiguous()
                 dwo = torch.zeros_like(w_orig)
