@@ -175,11 +175,18 @@ class _GeneratorFn(torch.autograd.Function):
         eng, dtype, keys = ctx.model._engine, ctx.dtype, ctx.keys
         P = dict(zip(keys, ctx.saved_tensors))
         s_enc, s_dec = ctx.saved
-        G = {}
+        # the optimizer registered the views of its flat gradient buffer (EnhancedCycleGAN._build_optimizers): accumulate there
+        # directly and hand autograd nothing to add
+        sinks = getattr(ctx.model, "_grad_sinks", None)
+        use_sink = sinks is not None and all(ctx.needs_input_grad[5:]) and all(k in sinks for k in keys)
+        G = eng.grad_sink(sinks, dy.device) if use_sink else {}
         dy = dy.contiguous().float()
         da = eng.decode_bwd(P, G, s_dec, dy, dtype)
         dx = eng.encode_bwd(P, G, s_enc, da, dtype, need_dx=ctx.needs_input_grad[4])
         ctx.saved = None
+        if use_sink:
+            eng.grad_sink_done(G)
+            return (None, None, None, None, dx) + (None,) * len(keys)
         grads = tuple(G.get(k) if ctx.needs_input_grad[5 + i] else None for i, k in enumerate(keys))
         return (None, None, None, None, dx) + grads
 

@@ -117,6 +117,8 @@ class EnhancedCycleGAN:
         self._broadcast_replica_state()
         for m in (self.G_AB, self.G_BA):
             m.invalidate_packed_weights()
+            # the generators' backward accumulates straight into the flat gradient buffer (generator_engine.GradSink)
+            m._grad_sinks = {k: p.grad for k, p in m.named_parameters()}
 
     def _broadcast_replica_state(self):
         """Data parallel: every rank must start from rank 0's parameters, Adam state and spectral-norm u / v buffers

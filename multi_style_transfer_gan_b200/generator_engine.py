@@ -47,6 +47,28 @@ class _StatsArena:
         return t
 
 
+class GradSink(dict):
+    """Parameter gradients accumulated straight into caller-owned fp32 buffers -- the views of the optimizer's flat gradient
+    buffer -- instead of fresh tensors that autograd then adds to .grad: per conv that was a zeros() for the packed gradient, a
+    zeros() for the unpacked one, the unpack, a dict add and autograd's accumulate (~1900 small launches per train step).  The
+    packed gradients of one backward come from ONE zeroed arena."""
+
+    def __init__(self, sinks, arena_floats, device):
+        super().__init__()
+        self.sinks = sinks
+        self.arena = torch.zeros(arena_floats, device=device, dtype=torch.float32) if arena_floats else None
+        self.pos, self.used = 0, 0
+
+    def scratch(self, n, device):
+        n = (n + 63) // 64 * 64             # (keeps every slice 256-byte aligned: the wgrad kernel reduces in 16-byte rows)
+        self.used += n
+        if self.arena is None or self.pos + n > self.arena.numel():
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        t = self.arena[self.pos:self.pos + n]
+        self.pos += n
+        return t
+
+
 class GeneratorEngine:
     def __init__(self, channels):
         c = self.c = channels
@@ -82,6 +104,7 @@ class GeneratorEngine:
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
+        self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
 
     def _versions(self, params, names):
         return tuple((params[n].data_ptr(), params[n]._version) for n in names)
@@ -278,12 +301,21 @@ class GeneratorEngine:
         """Accumulates weight / bias grads of conv `name` into G and returns dx (or None)."""
         g = self._g(name, dtype)
         m = self._master(P, name, dtype)
-        dw = torch.zeros_like(m)
-        db = torch.zeros(m.shape[1] if g.kind == "convT" else m.shape[0], device=m.device, dtype=torch.float32)
+        sink = G.sinks if isinstance(G, GradSink) else None
+        nb = m.shape[1] if g.kind == "convT" else m.shape[0]
         # A conv bias in front of an InstanceNorm has an EXACTLY zero gradient (the norm subtracts the plane mean: d(IN(y + b))/db
         # = 0; the reference's autograd produces ~1e-8 of rounding noise there).  Only the qkv / proj convs and the output conv
         # have live biases: the other 29 bias reductions of a generator backward are skipped (3.6 ms per train step).
         live_bias = name.endswith(".3.qkv") or name.endswith(".3.proj") or name == "output.0"
+        padded = name in ("initial.0", "output.0")          # (weights zero-padded to 4 / 8 image channels: unpack via a temporary)
+        direct = sink is not None and not padded
+        dw = sink[f"{name}.weight"] if direct else torch.zeros_like(m)
+        if not live_bias:
+            db = None
+        elif direct:
+            db = sink[f"{name}.bias"]
+        else:
+            db = torch.zeros(nb, device=m.device, dtype=torch.float32)
         if name == "initial.0" and dtype == torch.bfloat16 and x.shape[3] == 8 and x.shape[2] % 8 == 0:
             # Cin = 8 would send the weight gradient to the SIMT engine (1.5 ms per call at batch 8, 256^2: the largest
             # single item of the train step).  Zero-padding the IMAGE to one 64-channel block puts it on the tcgen05
@@ -291,16 +323,26 @@ class GeneratorEngine:
             x64 = torch.zeros(x.shape[:3] + (64,), device=x.device, dtype=x.dtype)
             x64[..., :8] = x
             dw64 = torch.zeros((m.shape[0], 64) + tuple(m.shape[2:]), device=m.device, dtype=torch.float32)
-            ConvGeom("conv", 64, g.Cout, g.k, g.stride, g.pad, g.dil).wgrad(x64, dy, dw64, db if live_bias else None, dy_c_off=dy_c_off)
+            ConvGeom("conv", 64, g.Cout, g.k, g.stride, g.pad, g.dil).wgrad(x64, dy, dw64, db, dy_c_off=dy_c_off)
             dw = dw64[:, :8].contiguous()
         else:
-            g.wgrad(x, dy, dw, db if live_bias else None, dy_c_off=dy_c_off)
+            g.wgrad(x, dy, dw, db, dy_c_off=dy_c_off,
+                    scratch=G.scratch(dw.numel(), m.device) if sink is not None else None)
         if name == "initial.0":
             dw = dw[:, :3].contiguous()
         if name == "output.0":
-            dw, db = dw[:3].contiguous(), db[:3].contiguous()
-        G[f"{name}.weight"] = dw if f"{name}.weight" not in G else G[f"{name}.weight"] + dw
-        G[f"{name}.bias"] = db if f"{name}.bias" not in G else G[f"{name}.bias"] + db
+            dw = dw[:3].contiguous()
+            db = db[:3].contiguous() if db is not None else None
+        if sink is not None:
+            if not direct:
+                sink[f"{name}.weight"].add_(dw)
+                if db is not None:
+                    sink[f"{name}.bias"].add_(db)
+        else:
+            if db is None:
+                db = torch.zeros(nb if name != "output.0" else 3, device=m.device, dtype=torch.float32)
+            G[f"{name}.weight"] = dw if f"{name}.weight" not in G else G[f"{name}.weight"] + dw
+            G[f"{name}.bias"] = db if f"{name}.bias" not in G else G[f"{name}.bias"] + db
         if not need_dx:
             return None
         return g.dgrad(dy, self._packed(P, name, "dgrad", dtype), in_hw or x.shape[1:3], out=dx_out,
@@ -331,6 +373,13 @@ class GeneratorEngine:
         da0 = self._conv_bwd(P, G, f"{s}.3.qkv", sv["a0"], dqkv, dtype)
         dy0 = ops.instnorm_bwd(sv["y0"], sv["st0"], da0, ACT_RELU)
         return self._conv_bwd(P, G, f"{s}.0", sv["a_in"], dy0, dtype)
+
+    def grad_sink(self, sinks, device):
+        """G argument of decode_bwd / encode_bwd that accumulates into `sinks` ({state_dict key: fp32 tensor})."""
+        return GradSink(sinks, self._arena_floats, device)
+
+    def grad_sink_done(self, G):
+        self._arena_floats = max(self._arena_floats, G.used)
 
     def decode_bwd(self, P, G, saved, dy, dtype):
         """dy: fp32 NCHW grad of the image.  Returns d(a) at the decoder input (NHWC)."""

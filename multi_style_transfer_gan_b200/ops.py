@@ -201,13 +201,14 @@ class ConvGeom:
             conv_raw(d, dy, wpd, None, out)
         return out
 
-    def wgrad(self, x, dy, dw, db=None, dy_c_off=0, ci_off=0, extra_flags=0):
-        """Accumulates into dw (fp32, PyTorch weight layout) and db (fp32 [Cout])."""
+    def wgrad(self, x, dy, dw, db=None, dy_c_off=0, ci_off=0, extra_flags=0, scratch=None):
+        """Accumulates into dw (fp32, PyTorch weight layout) and db (fp32 [Cout]).  scratch: optional ZEROED fp32 buffer of
+        dw.numel() elements for the packed gradient (a slice of the caller's arena instead of one allocation + memset per call)."""
         _dev(x)
         N, Hi, Wi, Ci_total = x.shape
         _, Ho, Wo, Cdy = dy.shape
         dt = _dt(x)
-        dwp = torch.zeros(dw.numel(), device=x.device, dtype=torch.float32)
+        dwp = scratch if scratch is not None else torch.zeros(dw.numel(), device=x.device, dtype=torch.float32)
         if self.kind == "conv":
             d = make_desc(dt, N, Hi, Wi, Ci_total, ci_off, self.Cin, Ho, Wo, Cdy, dy_c_off, self.Cout, Ho, Wo,
                           self.k, self.k, self.stride, self.pad, self.pad, self.dil, flags=extra_flags)
@@ -229,6 +230,13 @@ class ConvGeom:
 def bias_grad(dy, db, c_off=0, C=None):
     N, H, W, Ct = dy.shape
     C = Ct if C is None else C
+    if dy.dtype == torch.bfloat16 and C % 3 == 0 and C // 3 <= 256 and (C // 3) & (C // 3 - 1) == 0 and C // 3 >= 64:
+        # the qkv convs (3C channels): three power-of-two slices on the vectorised kernel (0.011 ms each) instead of one launch
+        # of the generic one (0.053 ms)
+        part = C // 3
+        for i in range(3):
+            _lib.call("msg_bias_grad", _dt(dy), _p(dy), N * H * W, Ct, c_off + i * part, part, _p(db[i * part:]), _stream())
+        return
     _lib.call("msg_bias_grad", _dt(dy), _p(dy), N * H * W, Ct, c_off, C, _p(db), _stream())
 
 
