@@ -103,11 +103,12 @@ class EnhancedCycleGAN:
         if self.lambda_style > 0 and style_loss is None:
             raise ValueError("lambda_style > 0 needs a style_loss (multi_style_transfer_gan_b200.style_loss.GramStyleLoss)")
         self._build_optimizers()
-        # use_graph: after `graph_warmup` eager steps the whole step (6 G + 10 D forwards, both backwards, the all-reduces and
-        # both Adam updates: ~2000 launches) is captured ONCE into a CUDA graph and replayed -- same kernels, same order, same
-        # results; the step was launch-bound (74 ms of kernels in a 93 ms step).  Inputs must keep their shape.
+        # use_graph: after `graph_warmup` eager steps the whole step (6 G + 10 D forwards, both backwards and both Adam updates:
+        # ~2000 launches) is captured ONCE into a CUDA graph and replayed -- same kernels, same order, same results; the step was
+        # launch-bound (74 ms of kernels in a 93 ms step).  Data parallel: the two NCCL all-reduces stay eager, between three
+        # graph segments that share one memory pool.  Inputs must keep their shape.
         self.use_graph, self.graph_warmup = bool(use_graph), int(graph_warmup)
-        self._graph, self._graph_io, self._eager_steps, self.graph_error = None, None, 0, None
+        self._graph, self._graph_io, self._eager_steps, self.graph_error, self._capture = None, None, 0, None, None
 
     def _build_optimizers(self):
         gp = [p for m in (self.G_AB, self.G_BA) for k, p in m.named_parameters()]
@@ -151,10 +152,21 @@ class EnhancedCycleGAN:
     def _sync_grads(self, opt):
         """One NCCL sum all-reduce over the optimizer's flat gradient buffer.  With ``self.comm_log`` set to a list, the call is
         bracketed by CUDA events on the launching stream (bench.py reports the time spent in the collective)."""
+        dp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        cap = getattr(self, "_capture", None)
+        if cap is not None:
+            # Capturing the step: the collective stays OUT of the graph.  The graph segment ends here, the replay runs the NCCL
+            # all-reduce eagerly between two segments, and the next segment starts (same memory pool, so tensors cross freely).
+            if dp or getattr(self, "segment_at_syncs", False):      # (segment_at_syncs: tests exercise the segmented replay on one GPU)
+                cap["graphs"][-1].capture_end()
+                cap["syncs"].append(opt)
+                nxt = torch.cuda.CUDAGraph()
+                nxt.capture_begin(pool=cap["graphs"][0].pool())
+                cap["graphs"].append(nxt)
+                return 1.0 / dist.get_world_size() if dp else 1.0
+            return 1.0
         log = getattr(self, "comm_log", None)
-        if torch.cuda.is_current_stream_capturing():
-            log = None                      # (events recorded during capture cannot be timed)
-        if log is None or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if log is None or not dp:
             return allreduce_flat_(opt.flat_grad)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -188,12 +200,21 @@ class EnhancedCycleGAN:
             io["A"].copy_(real_A, non_blocking=True)
             io["B"].copy_(real_B, non_blocking=True)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
             l0 = _lib.launches
+            cap = {"graphs": [torch.cuda.CUDAGraph()], "syncs": []}
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
             try:
-                with torch.cuda.graph(graph):
-                    io["keys"], io["vec"] = self._step_body(io["A"], io["B"])
-            except Exception as e:              # capture refused (e.g. a collective that cannot be captured): stay eager, loudly
+                with torch.cuda.stream(side):
+                    cap["graphs"][0].capture_begin()
+                    self._capture = cap
+                    try:
+                        io["keys"], io["vec"] = self._step_body(io["A"], io["B"])
+                    finally:
+                        self._capture = None
+                        cap["graphs"][-1].capture_end()
+                torch.cuda.current_stream().wait_stream(side)
+            except Exception as e:              # capture refused: stay eager, loudly
                 self.graph_error = repr(e)
                 torch.cuda.synchronize()
                 for o in (self.g_optimizer, self.d_optimizer):
@@ -205,11 +226,25 @@ class EnhancedCycleGAN:
             _lib.launches = l0
             for o in (self.g_optimizer, self.d_optimizer):
                 o.step_count -= 1               # the capture did not execute anything
-            self._graph, self._graph_io = graph, io
+            self._graph, self._graph_io = cap, io
         else:
             io["A"].copy_(real_A, non_blocking=True)
             io["B"].copy_(real_B, non_blocking=True)
-        self._graph.replay()
+        # replay: segment, [eager NCCL all-reduce of a flat gradient buffer, segment]*
+        cap = self._graph
+        log = getattr(self, "comm_log", None)
+        for i, gr in enumerate(cap["graphs"]):
+            if i > 0:
+                opt = cap["syncs"][i - 1]
+                if log is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    allreduce_flat_(opt.flat_grad)
+                    e1.record()
+                    log.append((e0, e1, opt.flat_grad.numel() * 4))
+                else:
+                    allreduce_flat_(opt.flat_grad)
+            gr.replay()
         _lib.launches += io["launches"]          # the replay launched exactly the kernels the capture recorded
         for o in (self.g_optimizer, self.d_optimizer):
             o.step_count += 1

@@ -257,24 +257,27 @@ def test_train_step_cuda_graph_matches_eager(golden):
     from multi_style_transfer_gan_b200.enhanced_train import EnhancedCycleGAN
     g = golden("train_step_c8_64.pt")
     runs = []
-    for use_graph in (False, True):
-        m = EnhancedCycleGAN(channels=8, num_transformer_blocks=1, precision="fp32", use_graph=use_graph, graph_warmup=1)
+    for use_graph in (False, True, "segmented"):
+        m = EnhancedCycleGAN(channels=8, num_transformer_blocks=1, precision="fp32", use_graph=bool(use_graph), graph_warmup=1)
+        m.segment_at_syncs = use_graph == "segmented"      # the data-parallel form: three graph segments, eager all-reduces between
         m.load_state_dicts(**g["init"])
         losses = [m.train_step(g["real_A"], g["real_B"]) for _ in range(4)]
         if use_graph:
             assert m._graph is not None and m.graph_error is None
+            assert len(m._graph["graphs"]) == (3 if use_graph == "segmented" else 1)
             assert m.g_optimizer.step_count == 4 and int(m.g_optimizer.step_dev.item()) == 4
         runs.append((losses, m.g_optimizer.flat.clone(), m.d_optimizer.flat.clone()))
     # Step 1 is eager in both runs and step 2 is the first replay: both agree to the noise of the order-free reductions.  From
     # step 3 on two EAGER runs of this c=8 network already differ by 5e-3 .. 5e-2 (measured, tools/graph_vs_eager.py: Adam's
     # first updates are ~lr * sign(g), so gradient noise on near-zero gradients flips whole updates) -- the graph run sits in
     # the same band, which is all that can be asserted there.
-    for step, (a, b) in enumerate(zip(runs[0][0], runs[1][0])):
-        tol = 1e-5 if step == 0 else 1e-4 if step == 1 else 0.15
-        for k in a:
-            assert abs(a[k] - b[k]) <= tol * abs(a[k]) + 1e-6, (step, k, a[k], b[k])
-    moved = float((runs[0][1] - runs[1][1]).abs().mean()), float((runs[0][2] - runs[1][2]).abs().mean())
-    assert moved[0] <= 2e-4 and moved[1] <= 8e-4, moved          # (4 steps x lr: 2e-4 / 8e-4 is "every update flipped")
+    for other in (1, 2):
+        for step, (a, b) in enumerate(zip(runs[0][0], runs[other][0])):
+            tol = 1e-5 if step == 0 else 1e-4 if step == 1 else 0.15
+            for k in a:
+                assert abs(a[k] - b[k]) <= tol * abs(a[k]) + 1e-6, (other, step, k, a[k], b[k])
+        moved = float((runs[0][1] - runs[other][1]).abs().mean()), float((runs[0][2] - runs[other][2]).abs().mean())
+        assert moved[0] <= 2e-4 and moved[1] <= 8e-4, moved          # (4 steps x lr: 2e-4 / 8e-4 is "every update flipped")
 
 
 def test_save_models_layout(tmp_path):
