@@ -255,14 +255,14 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
     H = W = args.size
     scale = (H * W) / 512 ** 2
     out = {}
-    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_la_stage_fwd")
+    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_la_stage_fwd", "msg_local_attn_fwd")
     conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in conv_keys) / args.steps
     conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in conv_keys) // args.steps
     fused_la = breakdown.get("msg_la_stage_fwd", {}).get("launches", 0) > 0
-    # algorithmic flops of those launches: conv + convT always; the LocalAttention bmm flops ride in the fused stage kernel
-    # (when every stage is fused) -- the stand-alone attention core launches (msg_local_attn_fwd) are not in this family
-    la_all_fused = fused_la and breakdown.get("msg_local_attn_fwd", {}).get("launches", 0) == 0
-    gflop = CONV_GFLOP_512 + ((GEN_GFLOP_512 - CONV_GFLOP_512) if la_all_fused else 0.0)
+    # algorithmic flops of those launches: conv + convT + the two LocalAttention contractions (198.844 GFLOP per
+    # 512x512 forward).  The attention products run inside the fused stage kernel (tcgen05) at C = 64 / 128 and in the
+    # stand-alone attention kernel (mma.sync) at C = 256: both are tensor-core launches of this family.
+    gflop = GEN_GFLOP_512
     flops = 3 * B_rank * gflop * scale * 1e9
     if conv_ms > 0:
         ach = flops / (conv_ms * 1e-3) / 1e12
@@ -270,6 +270,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
                                                                               and B_rank % 16 == 0) else (None, "not the profiled configuration"))
         out["roofline"] = {"bound": "tensor",
                            "kernel": "conv_tma_kernel + conv_slab_kernel + conv_shift_kernel" + (" + la_stage_kernel" if fused_la else "")
+                                     + (" + local_attn_fwd_tc_kernel" if breakdown.get("msg_local_attn_fwd", {}).get("launches", 0) else "")
                                      + " (every tensor-core launch of the step)",
                            "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": tnote,
@@ -361,7 +362,8 @@ def bench_train(cx, args, steps, warmup):
                                   + (f" + {args.lambda_style:g} x VGG-19 Gram style loss (random-init trunk)" if style else "")
                                   + f", fused Adam), c={c}, batch {B} per GPU at {S}x{S}",
                       "global_batch": B * cx.world, "parallelism": f"data-parallel x{cx.world}, 2 flat NCCL all-reduces per step",
-                      "schedule": "whole step replayed as one CUDA graph" if graphed else
+                      "schedule": (f"step replayed as {len(m._graph['graphs'])} CUDA-graph segment(s)"
+                                   + (", the NCCL all-reduces eager between them" if len(m._graph["graphs"]) > 1 else "")) if graphed else
                                   ("eager launches" + (f" (graph capture failed: {m.graph_error})" if m.graph_error else ""))},
            "images_per_sec": B * cx.world * 1e3 / ms,
            "gpu_launches_per_step": launches_per_step, "losses": losses,

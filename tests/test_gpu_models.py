@@ -84,7 +84,7 @@ def test_generator_golden_bf16(golden):
     stock = stock_bf16_error(g["state_dict"], g["x"], g["y"])
     print(f"bf16 end-to-end error vs fp32 reference: ours max {mine[0]:.3e} relL2 {mine[1]:.3e}; "
           f"stock torch bf16 max {stock[0]:.3e} relL2 {stock[1]:.3e}")
-    assert mine[1] <= 1.25 * stock[1] + 1e-3, (mine, stock)
+    assert mine[1] <= 1.0 * stock[1] + 1e-3, (mine, stock)      # at least as accurate as stock PyTorch bf16
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         y2 = make_G(16, 1, g["state_dict"]).eval()(g["x"].to(DEV))   # autocast selects the bf16 path
     assert torch.equal(y2, y) or parity_errors(y2, y)[1] < 1e-2
@@ -115,7 +115,7 @@ def test_config1_two_style_blend(golden, c, nb):
     mine = parity_errors(yb, g["y0"])
     stock = stock_bf16_error({k: v.detach().cpu() for k, v in Gb.state_dict().items()}, x.cpu(), g["y0"])
     print(f"config1 c={c} bf16: ours max {mine[0]:.3e} relL2 {mine[1]:.3e}; stock torch bf16 max {stock[0]:.3e} relL2 {stock[1]:.3e}")
-    assert mine[1] <= 1.25 * stock[1] + 1e-3, (mine, stock)
+    assert mine[1] <= 1.0 * stock[1] + 1e-3, (mine, stock)      # at least as accurate as stock PyTorch bf16
 
 
 def test_bad_sizes_raise():
