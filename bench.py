@@ -323,18 +323,30 @@ def bench_train(cx, args, steps, warmup):
     B, S = args.train_batch, args.train_size
     A = synth_images(B, S, S, seed=11 + cx.rank).pin_memory()
     Bm = synth_images(B, S, S, seed=12 + cx.rank).pin_memory()
-    # eager steps first (with use_graph: the two steps before the capture): the NCCL all-reduce is timed here, bracketed by CUDA
-    # events on the launching stream -- launches inside a replayed graph cannot be bracketed
-    m.comm_log = []
     n_eager = 2
     for _ in range(n_eager):
         m.train_step(A, Bm)
     torch.cuda.synchronize()
-    comm_ms = sum(a.elapsed_time(b) for a, b, _ in m.comm_log) / n_eager
-    comm_bytes = sum(n for _, _, n in m.comm_log) // n_eager
-    comm_calls = len(m.comm_log) // n_eager
-    comm_ms = cx.max_over_ranks(comm_ms)
-    m.comm_log = None
+    # the collectives on their own: the two flat-gradient all-reduces of a step (discriminators, generators), CUDA events on the
+    # launching stream, after two untimed rounds.  In the step the first one runs under the identity forwards.
+    comm_ms, comm_bytes, comm_calls = 0.0, 0, 0
+    if cx.world > 1:
+        bufs = [m.d_optimizer.flat_grad, m.g_optimizer.flat_grad]
+        for _ in range(2):
+            for b_ in bufs:
+                cx.dist.all_reduce(b_)
+        cx.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            for b_ in bufs:
+                cx.dist.all_reduce(b_)
+        c1.record()
+        torch.cuda.synchronize()
+        comm_ms = cx.max_over_ranks(c0.elapsed_time(c1) / 5)
+        comm_bytes, comm_calls = sum(b_.numel() * 4 for b_ in bufs), len(bufs)
+        for b_ in bufs:
+            b_.zero_()
     for _ in range(max(0, warmup - n_eager) + (1 if use_graph else 0)):      # (+ the capturing step)
         m.train_step(A, Bm)
     cx.barrier()
@@ -368,8 +380,8 @@ def bench_train(cx, args, steps, warmup):
            "images_per_sec": B * cx.world * 1e3 / ms,
            "gpu_launches_per_step": launches_per_step, "losses": losses,
            "nccl": {"ms_per_step": comm_ms, "bytes_per_step": comm_bytes, "calls_per_step": comm_calls,
-                    "how": "CUDA events around dist.all_reduce on the launching stream, max over ranks, on the eager steps before the "
-                           "graph capture"},
+                    "how": "the step's two flat-gradient all-reduces timed on their own (CUDA events on the launching stream, 5 rounds "
+                           "after 2 warm-up rounds, max over ranks); in the step the discriminator one runs under the identity forwards"},
            "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": 2 * A.numel() * 4, "d2h_bytes_per_step": 20},
            "breakdown_ms_per_step": {k: round(v["ms"] / bsteps, 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:12]},
            "breakdown_note": "one eager step after the timed region (same kernels)"}

@@ -105,7 +105,7 @@ class EnhancedCycleGAN:
         self._build_optimizers()
         # use_graph: after `graph_warmup` eager steps the whole step (6 G + 10 D forwards, both backwards and both Adam updates:
         # ~2000 launches) is captured ONCE into a CUDA graph and replayed -- same kernels, same order, same results; the step was
-        # launch-bound (74 ms of kernels in a 93 ms step).  Data parallel: the two NCCL all-reduces stay eager, between three
+        # launch-bound (74 ms of kernels in a 93 ms step).  Data parallel: the two NCCL all-reduces stay eager, between four
         # graph segments that share one memory pool.  Inputs must keep their shape.
         self.use_graph, self.graph_warmup = bool(use_graph), int(graph_warmup)
         self._graph, self._graph_io, self._eager_steps, self.graph_error, self._capture = None, None, 0, None, None
@@ -149,31 +149,48 @@ class EnhancedCycleGAN:
         for m in (self.G_AB, self.G_BA):
             m.invalidate_packed_weights()
 
+    @staticmethod
+    def _dp():
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _boundary(self, op):
+        """While the step is being captured: end the current graph segment, remember what the replay has to do eagerly at this
+        point, start the next segment (same memory pool, so tensors cross freely).  The NCCL collectives stay OUT of the graphs."""
+        cap = self._capture
+        cap["graphs"][-1].capture_end()
+        cap["ops"].append(op)
+        nxt = torch.cuda.CUDAGraph()
+        nxt.capture_begin(pool=cap["graphs"][0].pool())
+        cap["graphs"].append(nxt)
+
+    def _sync_begin(self, opt):
+        """Starts the sum all-reduce of the optimizer's flat gradient buffer (NCCL's own stream, after everything enqueued so far)
+        and returns a token for _sync_end; independent work issued in between runs under the collective."""
+        segment = self._dp() or getattr(self, "segment_at_syncs", False)     # (segment_at_syncs: one-GPU tests of the segmented replay)
+        if self._capture is not None:
+            if segment:
+                self._boundary(("begin", opt))
+            return None
+        return dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM, async_op=True) if self._dp() else None
+
+    def _sync_end(self, token):
+        """Waits for the all-reduce started by _sync_begin; returns the 1/world scale the fused Adam folds into its update."""
+        segment = self._dp() or getattr(self, "segment_at_syncs", False)
+        if self._capture is not None:
+            if segment:
+                self._boundary(("wait", None))
+        elif token is not None:
+            token.wait()
+        return 1.0 / dist.get_world_size() if self._dp() else 1.0
+
     def _sync_grads(self, opt):
-        """One NCCL sum all-reduce over the optimizer's flat gradient buffer.  With ``self.comm_log`` set to a list, the call is
-        bracketed by CUDA events on the launching stream (bench.py reports the time spent in the collective)."""
-        dp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        cap = getattr(self, "_capture", None)
-        if cap is not None:
-            # Capturing the step: the collective stays OUT of the graph.  The graph segment ends here, the replay runs the NCCL
-            # all-reduce eagerly between two segments, and the next segment starts (same memory pool, so tensors cross freely).
-            if dp or getattr(self, "segment_at_syncs", False):      # (segment_at_syncs: tests exercise the segmented replay on one GPU)
-                cap["graphs"][-1].capture_end()
-                cap["syncs"].append(opt)
-                nxt = torch.cuda.CUDAGraph()
-                nxt.capture_begin(pool=cap["graphs"][0].pool())
-                cap["graphs"].append(nxt)
-                return 1.0 / dist.get_world_size() if dp else 1.0
-            return 1.0
-        log = getattr(self, "comm_log", None)
-        if log is None or not dp:
-            return allreduce_flat_(opt.flat_grad)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        scale = allreduce_flat_(opt.flat_grad)
-        e1.record()
-        log.append((e0, e1, opt.flat_grad.numel() * 4))
-        return scale
+        """One blocking NCCL sum all-reduce over the optimizer's flat gradient buffer; returns the 1/world scale."""
+        if self._capture is not None:
+            if self._dp() or getattr(self, "segment_at_syncs", False):
+                self._boundary(("sync", opt))
+        elif self._dp():
+            dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size() if self._dp() else 1.0
 
     def train_step(self, real_A, real_B):
         """reference: enhanced_train.py:59-131 (order of the 6 G and 10 D forwards preserved, so the
@@ -201,7 +218,7 @@ class EnhancedCycleGAN:
             io["B"].copy_(real_B, non_blocking=True)
             torch.cuda.synchronize()
             l0 = _lib.launches
-            cap = {"graphs": [torch.cuda.CUDAGraph()], "syncs": []}
+            cap = {"graphs": [torch.cuda.CUDAGraph()], "ops": []}
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             try:
@@ -230,20 +247,20 @@ class EnhancedCycleGAN:
         else:
             io["A"].copy_(real_A, non_blocking=True)
             io["B"].copy_(real_B, non_blocking=True)
-        # replay: segment, [eager NCCL all-reduce of a flat gradient buffer, segment]*
+        # replay: segment, [eager NCCL op, segment]*
         cap = self._graph
-        log = getattr(self, "comm_log", None)
+        pending = None
         for i, gr in enumerate(cap["graphs"]):
             if i > 0:
-                opt = cap["syncs"][i - 1]
-                if log is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    allreduce_flat_(opt.flat_grad)
-                    e1.record()
-                    log.append((e0, e1, opt.flat_grad.numel() * 4))
-                else:
-                    allreduce_flat_(opt.flat_grad)
+                kind, opt = cap["ops"][i - 1]
+                if kind == "begin":
+                    pending = dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM, async_op=True) if self._dp() else None
+                elif kind == "sync":
+                    if self._dp():
+                        dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)
+                elif pending is not None:
+                    pending.wait()
+                    pending = None
             gr.replay()
         _lib.launches += io["launches"]          # the replay launched exactly the kernels the capture recorded
         for o in (self.g_optimizer, self.d_optimizer):
@@ -269,7 +286,10 @@ class EnhancedCycleGAN:
         d_fake_loss = (mse_to_const(fake_A_score, 0.0) + mse_to_const(fake_B_score, 0.0)) * 0.5
         d_loss = d_real_loss + d_fake_loss
         d_loss.backward()
-        self.d_optimizer.step(grad_scale=self._sync_grads(self.d_optimizer))
+        # Data parallel: the all-reduce of the discriminator gradients runs UNDER the two identity forwards of the generator phase,
+        # which do not touch the discriminators (same arithmetic as the reference's order -- D step first -- only the launch order
+        # differs); the D update waits for it.
+        d_sync = self._sync_begin(self.d_optimizer)
 
         # ---- generators (:87-123)
         self.g_optimizer.zero_grad()
@@ -278,6 +298,7 @@ class EnhancedCycleGAN:
         idt_A = G_BA(real_A)
         idt_B = G_AB(real_B)
         identity_loss = (l1(idt_A, real_A) + l1(idt_B, real_B)) * self.lambda_identity
+        self.d_optimizer.step(grad_scale=self._sync_end(d_sync))
         fake_A_score, _ = D_A(fake_A)
         fake_B_score, _ = D_B(fake_B)
         g_loss = mse_to_const(fake_A_score, 1.0) + mse_to_const(fake_B_score, 1.0)

@@ -259,12 +259,12 @@ def test_train_step_cuda_graph_matches_eager(golden):
     runs = []
     for use_graph in (False, True, "segmented"):
         m = EnhancedCycleGAN(channels=8, num_transformer_blocks=1, precision="fp32", use_graph=bool(use_graph), graph_warmup=1)
-        m.segment_at_syncs = use_graph == "segmented"      # the data-parallel form: three graph segments, eager all-reduces between
+        m.segment_at_syncs = use_graph == "segmented"      # the data-parallel form: four graph segments, the all-reduces eager between them
         m.load_state_dicts(**g["init"])
         losses = [m.train_step(g["real_A"], g["real_B"]) for _ in range(4)]
         if use_graph:
             assert m._graph is not None and m.graph_error is None
-            assert len(m._graph["graphs"]) == (3 if use_graph == "segmented" else 1)
+            assert len(m._graph["graphs"]) == (4 if use_graph == "segmented" else 1)
             assert m.g_optimizer.step_count == 4 and int(m.g_optimizer.step_dev.item()) == 4
         runs.append((losses, m.g_optimizer.flat.clone(), m.d_optimizer.flat.clone()))
     # Step 1 is eager in both runs and step 2 is the first replay: both agree to the noise of the order-free reductions.  From

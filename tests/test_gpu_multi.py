@@ -1,7 +1,7 @@
 """Two-GPU data-parallel train step over NCCL (skipped on a single-GPU box): one data-parallel step on two half batches
 equals one single-GPU step on the concatenated batch (IN statistics are per sample, the losses are batch means, the flat
 gradient all-reduce + 1/world in the fused Adam gives the global-batch gradient), the two replicas stay bit-identical, and
-the step also runs as a CUDA-graph replay (three graph segments, the two all-reduces eager between them)
+the step also runs as a CUDA-graph replay (four graph segments, the two all-reduces eager between them, the first one under the identity forwards)
 (enhanced_train.py:59-131)."""
 import os
 import socket
