@@ -295,6 +295,20 @@ int msg_spectral_norm(const float* w, int rows, int cols, float* u, float* v, in
                       float eps, float* sigma, void* stream);
 /* gradient through weight = weight_orig / sigma:
  * dw_orig += (dw - <dw, w_orig>/sigma * u v^T) / sigma  */
+/* the same for up to MSG_SN_MAX_BATCH weights in one launch (all seven convs of one discriminator forward,
+ * enhanced_generator.py:269-271): problem i = (w[i], rows[i], cols[i], u[i], v[i]) -> *sigma[i]. */
+#define MSG_SN_MAX_BATCH 8
+typedef struct {
+  const float* w[MSG_SN_MAX_BATCH];
+  float* u[MSG_SN_MAX_BATCH];
+  float* v[MSG_SN_MAX_BATCH];
+  float* sigma[MSG_SN_MAX_BATCH];
+  int rows[MSG_SN_MAX_BATCH];
+  int cols[MSG_SN_MAX_BATCH];
+  int n;
+} msg_sn_batch;
+int msg_spectral_norm_batched(const msg_sn_batch* b, int do_power_iter, float eps, void* stream);
+
 int msg_spectral_norm_bwd(const float* dw, const float* w_orig, const float* u, const float* v,
                           const float* sigma, int rows, int cols, float* dw_orig, float* scratch,
                           void* stream);

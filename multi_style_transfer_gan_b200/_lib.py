@@ -56,6 +56,15 @@ class ShiftDesc(ctypes.Structure):
         ("tile_rows", c_int), ("kb_same_slab", c_int * SHIFT_MAX_KBLOCKS), ("grp_row", c_int * SHIFT_MAX_GROUPS)]
 
 
+SN_MAX_BATCH = 8
+
+
+class SnBatch(ctypes.Structure):
+    """mirrors msg_sn_batch (include/msg_b200.h)"""
+    _fields_ = [("w", c_void_p * SN_MAX_BATCH), ("u", c_void_p * SN_MAX_BATCH), ("v", c_void_p * SN_MAX_BATCH),
+                ("sigma", c_void_p * SN_MAX_BATCH), ("rows", c_int * SN_MAX_BATCH), ("cols", c_int * SN_MAX_BATCH), ("n", c_int)]
+
+
 _P = c_void_p
 # name -> argtypes (everything returns int except msg_last_error)
 SIGNATURES = {
@@ -87,6 +96,7 @@ SIGNATURES = {
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],
     "msg_adam_step_dev": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, c_float, _P],
     "msg_spectral_norm": [_P, c_int, c_int, _P, _P, c_int, c_float, _P, _P],
+    "msg_spectral_norm_batched": [ctypes.POINTER(SnBatch), c_int, c_float, _P],
     "msg_spectral_norm_bwd": [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     "msg_gram": [c_int, _P, c_int, c_ll, c_int, _P, _P],
     "msg_gram_loss_fwd": [c_int, _P, c_int, c_ll, c_int, _P, c_float, _P, _P, _P],

@@ -47,6 +47,22 @@ class DiscriminatorEngine:
         ops.spectral_norm(w.detach(), rows, cols, u, v, training, sigma)
         return sigma, u.clone(), v.clone()
 
+    def _sigmas(self, P, training, save):
+        """The seven power iterations of one forward (IN PLACE on the u / v buffers, as the reference's forward pre-hooks do) in ONE
+        launch; returns {conv: (sigma[1], u snapshot, v snapshot)} -- the snapshots only when the backward needs them."""
+        w0 = P[f"{D_CONVS[0]}.weight_orig"]
+        sig = torch.empty(len(D_CONVS), device=w0.device, dtype=torch.float32)
+        probs = []
+        for i, n in enumerate(D_CONVS):
+            w = P[f"{n}.weight_orig"].detach()
+            probs.append((w, w.shape[0], w.numel() // w.shape[0], P[f"{n}.weight_u"], P[f"{n}.weight_v"], sig[i:i + 1]))
+        ops.spectral_norm_batched(probs, training)
+        out = {}
+        for i, n in enumerate(D_CONVS):
+            u, v = P[f"{n}.weight_u"], P[f"{n}.weight_v"]
+            out[n] = (sig[i:i + 1], u.clone() if save else u, v.clone() if save else v)
+        return out
+
     def forward(self, P, x, dtype, training, save):
         """x: fp32 NCHW [N,3,H,W] -> (score_map fp32 [N] (plane mean of the batch head),
         struct fp32 [N,1,h,w], saved)."""
@@ -54,7 +70,7 @@ class DiscriminatorEngine:
         N, Cx, H, W = x.shape
         if Cx != 3 or H % 16 or W % 16 or H < 32 or W < 32:
             raise RuntimeError(f"EnhancedDiscriminator: expected [N,3,H,W] with H,W multiples of 16 and >= 32, got {tuple(x.shape)}")
-        sn = {n: self._sigma(P, n, training) for n in D_CONVS}
+        sn = self._sigmas(P, training, save)
 
         def wp(n):
             return g[n].pack_fwd(self._master(P[f"{n}.weight_orig"].detach(), n, dtype), dtype, sn[n][0])

@@ -445,6 +445,15 @@ def spectral_norm(w2d_like, rows, cols, u, v, do_iter, sigma, eps=1e-12):
     _lib.call("msg_spectral_norm", _p(w2d_like), rows, cols, _p(u), _p(v), int(do_iter), float(eps), _p(sigma), _stream())
 
 
+def spectral_norm_batched(problems, do_iter, eps=1e-12):
+    """problems: [(w2d_like, rows, cols, u, v, sigma[1])], at most 8: one launch for all of them (csrc/elementwise.cu)"""
+    b = _lib.SnBatch()
+    b.n = len(problems)
+    for i, (w, rows, cols, u, v, sigma) in enumerate(problems):
+        b.w[i], b.u[i], b.v[i], b.sigma[i], b.rows[i], b.cols[i] = w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(), rows, cols
+    _lib.call("msg_spectral_norm_batched", ctypes.byref(b), int(do_iter), float(eps), _stream())
+
+
 def spectral_norm_bwd(dw, w_orig, u, v, sigma, rows, cols, dw_orig):
     scratch = torch.empty(1, device=dw.device, dtype=torch.float32)
     _lib.call("msg_spectral_norm_bwd", _p(dw), _p(w_orig), _p(u), _p(v), _p(sigma), rows, cols, _p(dw_orig), _p(scratch), _stream())
