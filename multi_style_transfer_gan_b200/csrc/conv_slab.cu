@@ -79,28 +79,31 @@ struct SlabParams {
 };
 
 // ---- compile-time description of the fused MultiScaleBlock forward program (slab.py: msb_program) ----------------
-// K blocks: dy in (-4,-2,-1,0,1,2,4) x channel block; taps of a K block in branch order b1 (dy == 0 only), then the three
-// horizontal taps of every 3x3 branch whose dilation d has |dy| in {0, d}.  Knowing this at compile time turns the
-// issue loop into straight-line code with immediate operands (~5 instructions per MMA instead of ~14): the generic
-// loop is ONE thread's serial instruction stream and was slower than the tensor pipe (ncu: issuer 85 % busy).
+// K blocks: dy in (0,-4,-2,-1,1,2,4) x channel block.  The centre row leads with its four UN-SHIFTED taps (b1 and the centres of
+// b2 / b3 / b4), then (b2: -1, +1), (b3: -2, +2), (b4: -4, +4); the other rows hold the three horizontal taps of the 3x3 branch
+// whose dilation is |dy|.  Knowing this at compile time turns the issue loop into straight-line code with immediate operands
+// (~5 instructions per MMA instead of ~14): the generic loop is ONE thread's serial instruction stream and was slower than
+// the tensor pipe (ncu: issuer 85 % busy).  The four un-shifted taps read the same slab view and write the four adjacent
+// accumulator slices: ONE MMA of N = C instead of four of N = C/4 (an MMA costs ~40 cycles whatever N < 128), and as the
+// first touch of every slice its first K step clears the accumulators.
 struct MsbTap { int sx, branch; };
-__host__ __device__ constexpr int msb_dy(int dyi) { return dyi == 0 ? -4 : dyi == 1 ? -2 : dyi == 2 ? -1 : dyi == 3 ? 0 : dyi == 4 ? 1 : dyi == 5 ? 2 : 4; }
-__host__ __device__ constexpr int msb_ntaps(int dyi) { return dyi == 3 ? 10 : 3; }
+__host__ __device__ constexpr int msb_dy(int dyi) { return dyi == 0 ? 0 : dyi == 1 ? -4 : dyi == 2 ? -2 : dyi == 3 ? -1 : dyi == 4 ? 1 : dyi == 5 ? 2 : 4; }
+__host__ __device__ constexpr int msb_ntaps(int dyi) { return dyi == 0 ? 10 : 3; }
 __host__ __device__ constexpr MsbTap msb_tap(int dyi, int j) {
-  if (dyi == 3) {                       // centre row: b1, then b2 / b3 / b4 with sx = -d, 0, d
-    if (j == 0) return MsbTap{0, 0};
-    const int b = 1 + (j - 1) / 3, d = b == 1 ? 1 : b == 2 ? 2 : 4;
-    return MsbTap{((j - 1) % 3 - 1) * d, b};
+  if (dyi == 0) {
+    if (j < 4) return MsbTap{0, j};
+    const int b = 1 + (j - 4) / 2, d = b == 1 ? 1 : b == 2 ? 2 : 4;
+    return MsbTap{((j - 4) % 2) ? d : -d, b};
   }
   const int dy = msb_dy(dyi), ad = dy < 0 ? -dy : dy;
   const int b = ad == 1 ? 1 : ad == 2 ? 2 : 3;
   return MsbTap{(j - 1) * ad, b};
 }
+__host__ __device__ constexpr bool msb_first(int dyi, int cb, int j) { return dyi == 0 && cb == 0 && j < 4; }
 // taps per K block (slab.py: msb_max_taps).  Measured on B200 for C = 128 (streamed weights): splitting the 10-tap centre row
 // into 4 + 4 + 2 (4 pipeline stages of 33 KB instead of 2 of 57 KB, but two more slab loads per tile) is SLOWER, 0.585 ->
 // 0.626 ms per 16 images: the kernel moves ~24 B/clk/SM from L2 either way, i.e. it is bound by L2 -> SM bytes, not latency.
 __host__ __device__ constexpr int msb_maxt(int) { return 32; }   // = no split for C = 64 and C = 128
-__host__ __device__ constexpr int msb_first_dyi(int branch) { return branch == 0 ? 3 : branch == 1 ? 2 : branch == 2 ? 1 : 0; }
 __host__ __device__ constexpr int msb_taps_before(int dyi) {   // taps of one channel block in the K blocks before row dyi
   int n = 0;
   for (int i = 0; i < dyi; ++i) n += msb_ntaps(i);
@@ -279,6 +282,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       // ---- specialised straight-line issue: every tap operand is an immediate --------------------------------
       constexpr int CB = MSBC / 64, Q = MSBC / 4, TAPU = Q * 8;      // weight tile of one tap in 16-byte units
       constexpr int MAXT = msb_maxt(MSBC);
+      static_assert(MAXT >= 4, "the merged centre taps must sit in one K block");
+      const uint32_t idesc_c = (idesc & ~(0x3fu << 17)) | ((uint32_t)(MSBC >> 3) << 17);      // N = MSBC
       const uint32_t hi = (uint32_t)(sw128_hi >> 32);
       const bool leader = elect_one();
       const uint32_t a_base = sA >> 4, a_step = (uint32_t)p.a_bytes >> 4;
@@ -307,12 +312,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                   const uint32_t ar = a0 + (uint32_t)r * row_u, dr = tacc + (uint32_t)(r * MSBC);
 #pragma unroll
                   for (int j = j0; j < (j0 + MAXT < msb_ntaps(dyi) ? j0 + MAXT : msb_ntaps(dyi)); ++j) {
+                    if (dyi == 0 && j < 4) {
+                      if (j == 0) {          // the four un-shifted taps: one N = MSBC MMA per K step over the four adjacent weight tiles
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                          umma_bf16_lo(dr, ar + (uint32_t)(4 * 8 + 2 * ks), b0 + (uint32_t)(2 * ks), hi, idesc_c, !(cb == 0 && ks == 0));
+                      }
+                      continue;
+                    }
                     const MsbTap tap = msb_tap(dyi, j);
-                    const bool first = cb == 0 && j == 0 && dyi == msb_first_dyi(tap.branch);   // first tap of its accumulator slice
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                       umma_bf16_lo(dr + (uint32_t)(tap.branch * Q), ar + (uint32_t)((4 + tap.sx) * 8 + 2 * ks),
-                                   b0 + (uint32_t)((j - j0) * TAPU + 2 * ks), hi, idesc, !(first && ks == 0));
+                                   b0 + (uint32_t)((j - j0) * TAPU + 2 * ks), hi, idesc, true);
                   }
                 }
                 umma_commit(empty_bar(s));
@@ -594,7 +606,7 @@ bool is_msb_program(const msg_slab_desc* d) {
         for (int j = j0; j < msb_ntaps(dyi) && j < j0 + MAXT; ++j, ++tp) {
           const MsbTap t = msb_tap(dyi, j);
           if (d->tap_sx[tp] != t.sx || d->tap_acc_col[tp] != t.branch * Q) return false;
-          if (d->tap_first[tp] != (cb == 0 && j == 0 && dyi == msb_first_dyi(t.branch) ? 1 : 0)) return false;
+          if (d->tap_first[tp] != (msb_first(dyi, cb, j) ? 1 : 0)) return false;
         }
       }
   return kb == d->n_kblocks && d->kb_tap_begin[kb] == tp;

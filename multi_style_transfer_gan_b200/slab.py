@@ -55,7 +55,10 @@ def msb_program(C, max_taps=None):
     kblocks = []
     if max_taps is None:
         max_taps = msb_max_taps(C)
-    for dy in (-4, -2, -1, 0, 1, 2, 4):
+    # The centre row comes FIRST and its four un-shifted taps (the 1x1 branch and the centres of the three 3x3 branches) lead:
+    # they read the same slab view and write the four adjacent accumulator slices, so the specialised kernels issue them as ONE
+    # N = C MMA (csrc/conv_slab.cu: 28 -> 25 MMAs per K step) -- and as the first touch of every slice it needs no zeroing.
+    for dy in (0, -4, -2, -1, 1, 2, 4):
         for cb in range(C // 64):
             taps = []
             for b, (k, dil) in enumerate(branches):
@@ -64,6 +67,8 @@ def msb_program(C, max_taps=None):
                         continue
                     for kw in range(k):
                         taps.append(((kw - k // 2) * dil, b * q, 0, (b, kh, kw, cb)))
+            if dy == 0:
+                taps = [t for t in taps if t[0] == 0] + [t for t in taps if t[0] != 0]
             for i in range(0, len(taps), max_taps):          # a long tap list re-loads the slab (rare: C=256 centre row)
                 kblocks.append((dy, cb, taps[i:i + max_taps]))
     return SlabProgram(C, C, C, q, 4, False, kblocks)
