@@ -268,6 +268,18 @@ int msg_blend_outputs(const float* const* ys, const float* w, int S, const float
                       float gain, int do_clip, float clip_lo, float clip_hi, long long numel,
                       float* out_f32, uint8_t* out_u8, void* stream);
 
+/* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
+ * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):
+ * out fp32 NCHW [N,3,H,W] = (v / 255 - 0.5) / 0.5.  canvas (optional, may be NULL): the pasted uint8 canvas [N,H,W,3].
+ * With h == H, w == W and zero offsets it is the plain uint8 -> normalised conversion. */
+int msg_u8_canvas_to_nchw(const uint8_t* img, int N, int h, int w, int H, int W, int off_y, int off_x, int fill,
+                          float* out, uint8_t* canvas, void* stream);
+/* "simple" mode strength blend in uint8 space (batch_process_images.py:304-310, gan_login_gui.py:826):
+ * out = uint8(clip(orig * (1 - s) + styled * s, 0, 255)), float64 arithmetic, truncating conversion.
+ * orig / out: NHWC uint8 [N,H,W,3]; styled: NCHW uint8 [N,3,H,W] (msg_blend_outputs' uint8 result). */
+int msg_u8_strength_blend(const uint8_t* orig_nhwc, const uint8_t* styled_nchw, int N, int H, int W, double strength,
+                          uint8_t* out_nhwc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * losses (enhanced_train.py:49-52): mean-reduced MSE / L1, forward value and input gradient.
  * loss_out: device fp32 scalar, ACCUMULATED into (+= scale * mean(...)); grad_a = scale*d/da.

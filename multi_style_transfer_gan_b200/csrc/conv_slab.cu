@@ -772,7 +772,9 @@ extern "C" int msg_conv_slab(const msg_slab_desc* d, const void* x, const void* 
   // re-reads of the C = 64 MSB program (1.8 -> 0.6 GB) but not its time (shared-memory bound: 0.79 -> 0.80 ms), is neutral for
   // C = 128 (0.50 -> 0.49 ms) and costs where an image has few tiles (statistics flushed with fp64 atomics every few tiles:
   // transposed-conv phases 0.49 -> 0.82 ms, 7x7 input conv 0.40 -> 0.45 ms).
-  p.interleave = env_il >= 0 ? env_il : 0;
+  // Round 2: on for the two specialised MSB programs -- same time, but 2-3x less DRAM traffic for the other streams' kernels
+  // that run beside them in the stylise step (ncu: 1.80 -> ~0.6 GB read for a 0.54 GB input at C = 64).
+  p.interleave = env_il >= 0 ? env_il : (spec == 64 || spec == 128 ? 1 : 0);
   const int fixed = fixed_for(p.epi_groups);
   int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;

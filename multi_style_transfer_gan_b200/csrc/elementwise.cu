@@ -443,6 +443,71 @@ adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   }
 }
 
+// ---- uint8 pre / post-processing on the device (batch_process_images.py:193-205, 287-291, 304-310) ----------------------
+// canvas paste + ToTensor + Normalize(0.5, 0.5): out[n][c][Y][X] = (v / 255 - 0.5) / 0.5 with v = img[n][Y-oy][X-ox][c] inside
+// the pasted image and `fill` (the white canvas) outside.  torchvision's arithmetic: ToTensor divides by 255 in fp32, Normalize
+// subtracts 0.5 and divides by 0.5 in fp32.
+__global__ void __launch_bounds__(EW_TPB)
+u8_canvas_to_nchw_kernel(const uint8_t* __restrict__ img, int N, int h, int w, int H, int W, int oy, int ox, int fill,
+                         float* __restrict__ out, uint8_t* __restrict__ canvas) {
+  const long long total = (long long)N * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % W);
+    long long t = idx / W;
+    const int Y = (int)(t % H), n = (int)(t / H);
+    const int y = Y - oy, x = X - ox;
+    int v[3] = {fill, fill, fill};
+    if (y >= 0 && y < h && x >= 0 && x < w) {
+      const uint8_t* s = img + (((size_t)n * h + y) * w + x) * 3;
+      v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = __fdiv_rn((float)v[c], 255.f);
+      out[(((size_t)n * 3 + c) * H + Y) * W + X] = __fdiv_rn(f - 0.5f, 0.5f);
+      if (canvas) canvas[(((size_t)n * H + Y) * W + X) * 3 + c] = (uint8_t)v[c];
+    }
+  }
+}
+// "simple" mode strength blend in uint8 space: out = uint8(clip(orig * (1 - s) + styled * s, 0, 255)) -- numpy's float64
+// arithmetic and truncating astype, batch_process_images.py:304-310.  orig / out: NHWC uint8 (PIL layout); styled: NCHW uint8.
+__global__ void __launch_bounds__(EW_TPB)
+u8_strength_blend_kernel(const uint8_t* __restrict__ orig, const uint8_t* __restrict__ styled, int N, int H, int W, double s,
+                         uint8_t* __restrict__ out) {
+  const long long total = (long long)N * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % W);
+    long long t = idx / W;
+    const int Y = (int)(t % H), n = (int)(t / H);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = (size_t)idx * 3 + c;
+      const double st = (double)styled[(((size_t)n * 3 + c) * H + Y) * W + X];
+      double r = __dadd_rn(__dmul_rn((double)orig[o], 1.0 - s), __dmul_rn(st, s));     // (no fma contraction: numpy rounds each product)
+      r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
+      out[o] = (uint8_t)r;
+    }
+  }
+}
+
+extern "C" int msg_u8_canvas_to_nchw(const uint8_t* img, int N, int h, int w, int H, int W, int off_y, int off_x, int fill,
+                                     float* out, uint8_t* canvas, void* stream) {
+  MSG_REQUIRE(img && out && N > 0 && h > 0 && w > 0 && H > 0 && W > 0, MSG_ERR_SHAPE, "u8_canvas_to_nchw: bad arguments");
+  MSG_REQUIRE(off_y >= 0 && off_x >= 0 && off_y + h <= H && off_x + w <= W && fill >= 0 && fill <= 255, MSG_ERR_SHAPE,
+              "u8_canvas_to_nchw: the %dx%d image at (%d, %d) does not fit the %dx%d canvas", h, w, off_y, off_x, H, W);
+  const long long total = (long long)N * H * W;
+  u8_canvas_to_nchw_kernel<<<ew_blocks(total, 2), EW_TPB, 0, as_stream(stream)>>>(img, N, h, w, H, W, off_y, off_x, fill, out, canvas);
+  return check_launch("u8_canvas_to_nchw_kernel");
+}
+
+extern "C" int msg_u8_strength_blend(const uint8_t* orig_nhwc, const uint8_t* styled_nchw, int N, int H, int W, double strength,
+                                     uint8_t* out_nhwc, void* stream) {
+  MSG_REQUIRE(orig_nhwc && styled_nchw && out_nhwc && N > 0 && H > 0 && W > 0, MSG_ERR_SHAPE, "u8_strength_blend: bad arguments");
+  const long long total = (long long)N * H * W;
+  u8_strength_blend_kernel<<<ew_blocks(total, 2), EW_TPB, 0, as_stream(stream)>>>(orig_nhwc, styled_nchw, N, H, W, strength, out_nhwc);
+  return check_launch("u8_strength_blend_kernel");
+}
+
 extern "C" int msg_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr,
                                  float beta1, float beta2, float eps, int* step_dev, float grad_scale,
                                  void* stream) {

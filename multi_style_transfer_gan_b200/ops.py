@@ -435,6 +435,29 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
               float(eps), int(step), float(grad_scale), _stream())
 
 
+def u8_canvas_to_nchw(img_u8, H=None, W=None, off_y=0, off_x=0, fill=255, want_canvas=False):
+    """uint8 [N,h,w,3] (PIL layout, on the device) -> fp32 NCHW [N,3,H,W] normalised to [-1,1] after pasting on an HxW canvas
+    (batch_process_images.py:193-205); with want_canvas also the uint8 canvas [N,H,W,3]."""
+    _dev(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3 and img_u8.is_contiguous()
+    N, h, w, _ = img_u8.shape
+    H, W = (h if H is None else H), (w if W is None else W)
+    out = torch.empty((N, 3, H, W), device=img_u8.device, dtype=torch.float32)
+    canvas = torch.empty((N, H, W, 3), device=img_u8.device, dtype=torch.uint8) if want_canvas else None
+    _lib.call("msg_u8_canvas_to_nchw", _p(img_u8), N, h, w, H, W, int(off_y), int(off_x), int(fill), _p(out), _p(canvas), _stream())
+    return (out, canvas) if want_canvas else out
+
+
+def u8_strength_blend(orig_nhwc, styled_nchw, strength):
+    """uint8(clip(orig * (1 - s) + styled * s, 0, 255)) (batch_process_images.py:304-310); orig NHWC, styled NCHW -> NHWC."""
+    _dev(orig_nhwc)
+    N, H, W, _ = orig_nhwc.shape
+    assert orig_nhwc.dtype == styled_nchw.dtype == torch.uint8 and tuple(styled_nchw.shape) == (N, 3, H, W)
+    out = torch.empty_like(orig_nhwc)
+    _lib.call("msg_u8_strength_blend", _p(orig_nhwc.contiguous()), _p(styled_nchw.contiguous()), N, H, W, float(strength), _p(out), _stream())
+    return out
+
+
 def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
     """as adam_step with the step count in device memory (int32 tensor, incremented by the call): graph-replayable"""
     _lib.call("msg_adam_step_dev", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),

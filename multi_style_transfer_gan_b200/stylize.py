@@ -119,7 +119,9 @@ class MultiStyleStylizer:
 
     @torch.no_grad()
     def __call__(self, x, weights, w_x=0.0, gain=1.0, clip=None, out_uint8=False, out=None):
-        """x: float32 [B,3,H,W] in [-1,1], on the device or on the host (pinned for overlap).
+        """x: float32 [B,3,H,W] in [-1,1], or uint8 [B,H,W,3] (PIL layout: ToTensor + Normalize(0.5, 0.5) then run on the
+        device, batch_process_images.py:287-291 -- a quarter of the host-to-device bytes), on the device or on the host
+        (pinned for overlap).
         Returns the blended fp32 images [B,3,H,W] on the device, or -- with out_uint8=True -- the
         uint8 images ((v+1)/2 -> clamp -> *255, direct_transform.py:66-71) in `out` (host or device
         uint8 tensor [B,3,H,W]; allocated on the device if None)."""
@@ -133,8 +135,12 @@ class MultiStyleStylizer:
         B = x.shape[0]
         mb = self.micro_batch
         host_in = not x.is_cuda
+        u8_in = x.dtype == torch.uint8
+        if u8_in and (x.dim() != 4 or x.shape[3] != 3):
+            raise RuntimeError("MultiStyleStylizer: uint8 input must be [B,H,W,3]")
+        hw = tuple(x.shape[1:3]) if u8_in else tuple(x.shape[2:])
         if out is None:
-            out = torch.empty((B, 3) + tuple(x.shape[2:]), device=self.device,
+            out = torch.empty((B, 3) + hw, device=self.device,
                               dtype=torch.uint8 if out_uint8 else torch.float32)
         host_out = not out.is_cuda
         cur = torch.cuda.current_stream(self.device)
@@ -163,6 +169,8 @@ class MultiStyleStylizer:
             if ev is not None:
                 cur.wait_event(ev)
                 xi.record_stream(cur)
+            if u8_in:
+                xi = ops.u8_canvas_to_nchw(xi.contiguous())
             dst = None if host_out else out[lo:hi]      # device result: the blend writes it in place
             if dst is None:
                 dst = torch.empty((hi - lo,) + tuple(out.shape[1:]), device=self.device, dtype=out.dtype)

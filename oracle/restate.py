@@ -305,6 +305,26 @@ def to_uint8_image(y):
     return (((y + 1.0) / 2.0).clamp(0, 1) * 255).to(torch.uint8)
 
 
+def letterbox_normalize(img_u8, H, W, off_y, off_x, fill=255):
+    """batch_process_images.py:193-205 (and :270-291): paste the resized uint8 image [h,w,3] on a white HxW canvas at the
+    centring offsets, then transforms.ToTensor() + Normalize((0.5,)*3, (0.5,)*3).  Returns (fp32 [3,H,W], uint8 canvas [H,W,3]).
+    (The LANCZOS resize in front of it is PIL's, host side, out of scope.)"""
+    h, w, _ = img_u8.shape
+    canvas = torch.full((H, W, 3), fill, dtype=torch.uint8)
+    canvas[off_y:off_y + h, off_x:off_x + w] = img_u8
+    t = canvas.permute(2, 0, 1).to(torch.float32).div(255)          # ToTensor
+    return (t - 0.5) / 0.5, canvas                                   # Normalize
+
+
+def strength_blend_u8(orig_u8, styled_u8, strength):
+    """batch_process_images.py:304-310 ('simple' mode; gan_login_gui.py:826): numpy float64 arithmetic, clip, truncating astype.
+    orig_u8, styled_u8: uint8 [H,W,3] arrays / tensors."""
+    import numpy as np
+    o, s = np.asarray(orig_u8), np.asarray(styled_u8)
+    r = o * (1 - strength) + s * strength
+    return torch.from_numpy(np.clip(r, 0, 255).astype(np.uint8))
+
+
 # --------------------------------------------------------------------------------------------
 # pretrain.Generator (pretrain.py:60-97): 4x[Conv4x4 s2 (+BN) + LeakyReLU 0.2] -> 4x[ConvT4x4 s2 (+BN) + ReLU], tanh
 # --------------------------------------------------------------------------------------------

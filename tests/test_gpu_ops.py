@@ -295,3 +295,45 @@ def test_pooling_and_act_bwd():
     assert_parity(nchw(dx), x.grad, 1e-6, "maxpool bwd")
     m = ops.avgpool_fwd(nhwc(x.detach(), torch.float32))
     assert_parity(m, x.detach().mean((2, 3)), 1e-5, "avgpool")
+
+
+@pytest.mark.parametrize("h,w,H,W", [(256, 171, 256, 256), (144, 256, 256, 256), (64, 64, 64, 64), (17, 33, 48, 80)])
+def test_u8_canvas_to_nchw_and_strength_blend_bit_exact(h, w, H, W):
+    """device-side uint8 pre / post-processing (msg_u8_canvas_to_nchw, msg_u8_strength_blend) vs the oracle's restatement of
+    batch_process_images.py:193-205, 287-291, 304-310: integer / byte work, bit-exact (the fp32 normalisation too: the same
+    two IEEE divisions)."""
+    from multi_style_transfer_gan_b200 import ops
+    from oracle import restate as R
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    imgs = torch.randint(0, 256, (3, h, w, 3), generator=g, dtype=torch.uint8)
+    oy, ox = (H - h) // 2, (W - w) // 2
+    x, canvas = ops.u8_canvas_to_nchw(imgs.to(DEV), H, W, oy, ox, want_canvas=True)
+    styled = torch.randint(0, 256, (3, 3, H, W), generator=g, dtype=torch.uint8)
+    for n in range(3):
+        xr, cr = R.letterbox_normalize(imgs[n], H, W, oy, ox)
+        assert torch.equal(x[n].cpu(), xr)
+        assert torch.equal(canvas[n].cpu(), cr)
+    for s in (0.0, 0.35, 0.8, 1.0):
+        out = ops.u8_strength_blend(canvas, styled.to(DEV), s).cpu()
+        for n in range(3):
+            assert torch.equal(out[n], R.strength_blend_u8(canvas[n].cpu(), styled[n].permute(1, 2, 0).contiguous(), s)), (s, n)
+    with pytest.raises(Exception):
+        ops.u8_canvas_to_nchw(imgs.to(DEV), h - 1, W, 0, 0)
+
+
+def test_stylizer_accepts_uint8_images():
+    """uint8 [B,H,W,3] input (host or device) == the same images normalised on the host as the reference does"""
+    from multi_style_transfer_gan_b200.enhanced_generator import EnhancedGenerator
+    from multi_style_transfer_gan_b200.stylize import MultiStyleStylizer
+    gens = []
+    for s in range(2):
+        torch.manual_seed(s)
+        gens.append(EnhancedGenerator(16, 1).to(DEV))
+    sty = MultiStyleStylizer(gens, precision="bf16", micro_batch=2)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 64, 48, 3), generator=g, dtype=torch.uint8)
+    xf = ((u8.permute(0, 3, 1, 2).float() / 255) - 0.5) / 0.5
+    ref = sty(xf.to(DEV), [0.6, 0.4], out_uint8=True)
+    for inp in (u8, u8.pin_memory(), u8.to(DEV)):
+        out = sty(inp, [0.6, 0.4], out_uint8=True)
+        assert torch.equal(out, ref)
