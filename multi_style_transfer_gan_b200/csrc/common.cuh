@@ -73,6 +73,20 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return t;
 }
 
+// Running sum kept as an unevaluated (hi, lo) pair of floats (Knuth TwoSum): ~2^-44 relative, in the 8 bytes of the double it
+// replaces.  The conv epilogues add their fixed-order 32-row fp32 partial sums into per-warp running column sums once per tile;
+// as fp64 adds those were the hottest stall of the 7x7 input conv's epilogue ("math pipe throttle" on the two DADDs: 26 % of
+// all stall samples, ncu) -- B200's FP64 pipe is narrow.  The pair is converted to fp64 only when a CTA flushes an image.
+__device__ __forceinline__ void f2sum_add(float2& s, float x) {
+  const float a = s.x;
+  const float t = __fadd_rn(a, x);
+  const float bb = __fsub_rn(t, a);
+  const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(t, bb)), __fsub_rn(x, bb));
+  s.x = t;
+  s.y = __fadd_rn(s.y, err);
+}
+__device__ __forceinline__ double f2sum_value(float2 s) { return (double)s.x + (double)s.y; }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case MSG_ACT_RELU: return v > 0.f ? v : 0.f;

@@ -169,18 +169,18 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int row = q * 32 + lane;                // slab pixel held by this thread (TMEM lane)
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
-    double* wsum = reinterpret_cast<double*>(gen + (sSum - base)) + q * 128;  // [2][64], fp64 above the 32-row partials
+    float2* wsum = reinterpret_cast<float2*>(gen + (sSum - base)) + q * 128;  // [2][64], fp64 above the 32-row partials
     float* tr = reinterpret_cast<float*>(gen + (sTr - base)) + q * 1056;      // [32][33]
-    for (int i = lane; i < 128; i += 32) wsum[i] = 0.0;
+    for (int i = lane; i < 128; i += 32) wsum[i] = make_float2(0.f, 0.f);
     __syncwarp();
     int stat_img = -1;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < d.n_out; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
-          atomicAdd(st, wsum[c]);
-          atomicAdd(st + 1, wsum[64 + c]);
-          wsum[c] = 0.0; wsum[64 + c] = 0.0;
+          atomicAdd(st, f2sum_value(wsum[c]));
+          atomicAdd(st + 1, f2sum_value(wsum[64 + c]));
+          wsum[c] = make_float2(0.f, 0.f); wsum[64 + c] = make_float2(0.f, 0.f);
         }
       }
       __syncwarp();
@@ -250,7 +250,7 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             float cs = 0.f, css = 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) { const float xv = tr[lane * 33 + r]; cs += xv; css = fmaf(xv, xv, css); }
-            if (lane < oc) { wsum[oc0 + lane] += (double)cs; wsum[64 + oc0 + lane] += (double)css; }
+            if (lane < oc) { f2sum_add(wsum[oc0 + lane], cs); f2sum_add(wsum[64 + oc0 + lane], css); }
           }
           __syncwarp();
         }

@@ -426,19 +426,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* stage_w = stage_gen + grp * EPI_STAGE + q * (32 * STAGE_PITCH);
     const int cmax = d.n_store;                   // columns actually stored (<= Ntot)
     const int WS = d.Ntot;                        // sums in [0, WS), sums of squares in [WS, 2 WS)
-    double* wsum = reinterpret_cast<double*>(red + grp * (p.epi_red / 4)) + q * 2 * WS;   // [2][256] running column sums of this warp (fp64 above the
+    float2* wsum = reinterpret_cast<float2*>(red + grp * (p.epi_red / 4)) + q * 2 * WS;   // [2][256] running column sums of this warp (fp64 above the
                                                                // fixed-order 32-row fp32 partials: grouping-independent)
     float* tr = red + grp * (p.epi_red / 4) + 4 * 4 * WS + q * 1088;   // [32][34] transpose scratch of this warp (after the 4 warps' fp64 sums)
-    for (int i = lane; i < 2 * WS; i += 32) wsum[i] = 0.0;
+    for (int i = lane; i < 2 * WS; i += 32) wsum[i] = make_float2(0.f, 0.f);
     __syncwarp();
     int stat_img = -1;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < cmax; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + c) * 2;
-          atomicAdd(st, wsum[c]);
-          atomicAdd(st + 1, wsum[WS + c]);
-          wsum[c] = 0.0; wsum[WS + c] = 0.0;
+          atomicAdd(st, f2sum_value(wsum[c]));
+          atomicAdd(st + 1, f2sum_value(wsum[WS + c]));
+          wsum[c] = make_float2(0.f, 0.f); wsum[WS + c] = make_float2(0.f, 0.f);
         }
       }
       __syncwarp();
@@ -518,8 +518,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               const float cs = s2.x + s2.y, css = q2.x + q2.y;
               __syncwarp();
               if (cg + h * 32 + lane < WS) {
-                wsum[cg + h * 32 + lane] += (double)cs;
-                wsum[WS + cg + h * 32 + lane] += (double)css;
+                f2sum_add(wsum[cg + h * 32 + lane], cs);
+                f2sum_add(wsum[WS + cg + h * 32 + lane], css);
               }
             }
           }

@@ -291,18 +291,18 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // running column sums of this warp, [2][256], in fp64: the 32-row partial sums are formed in fp32 in a fixed
     // order, everything above that is fp64, so an image's statistics do not depend on how tiles were grouped per CTA
     // (batch size, epilogue groups) beyond fp64 rounding
-    double* wsum = reinterpret_cast<double*>(red + grp * (EPI_FIXED / 4)) + q * 512;
+    float2* wsum = reinterpret_cast<float2*>(red + grp * (EPI_FIXED / 4)) + q * 512;
     float* tr = red + grp * (EPI_FIXED / 4) + 4096 + q * 1088;            // [32][34] transpose scratch of this warp
-    for (int i = lane; i < 512; i += 32) wsum[i] = 0.0;
+    for (int i = lane; i < 512; i += 32) wsum[i] = make_float2(0.f, 0.f);
     __syncwarp();
     int stat_img = -1, stat_nt = -1, stat_cmax = 0;
     auto flush_stats = [&]() {
       if (stat_img >= 0) {
         for (int c = lane; c < stat_cmax; c += 32) {
           double* st = p.stats + ((size_t)stat_img * d.Co_total + d.co_off + stat_nt * BN + c) * 2;
-          atomicAdd(st, wsum[c]);
-          atomicAdd(st + 1, wsum[256 + c]);
-          wsum[c] = 0.0; wsum[256 + c] = 0.0;
+          atomicAdd(st, f2sum_value(wsum[c]));
+          atomicAdd(st + 1, f2sum_value(wsum[256 + c]));
+          wsum[c] = make_float2(0.f, 0.f); wsum[256 + c] = make_float2(0.f, 0.f);
         }
       }
       __syncwarp();
@@ -385,8 +385,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               }
               const float cs = s2.x + s2.y, css = q2.x + q2.y;
               __syncwarp();
-              wsum[cg + h * 32 + lane] += (double)cs;
-              wsum[256 + cg + h * 32 + lane] += (double)css;
+              f2sum_add(wsum[cg + h * 32 + lane], cs);
+              f2sum_add(wsum[256 + cg + h * 32 + lane], css);
             }
           }
         }
