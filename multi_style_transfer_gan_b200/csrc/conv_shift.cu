@@ -27,7 +27,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // TMA, MMA, 2 x 4 epilogue warps (group g drains TMEM accumulator buffer g: every other tile)
 constexpr int A_BYTES = BM * 128;
 
 
@@ -37,6 +37,7 @@ struct ShiftParams {
   void* y;
   double* stats;
   int stages, tmem_cols, b_bytes, b_rows, Wv, segs, ex_pitch;
+  int groups;          // epilogue groups (1 or 2)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -50,12 +51,12 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sB = base;                                   // resident weights [b_rows][128 B], SW128
   const uint32_t sA = sB + p.b_bytes;                         // slab ring
-  const uint32_t sEx = sA + S * A_BYTES;                      // exchange tile [128][Ntot + 4] floats
-  const uint32_t sSum = (sEx + BM * p.ex_pitch * 4 + 7u) & ~7u;  // per-warp column sums [4][2][64] doubles
-  const uint32_t sTr = sSum + 4 * 128 * 8;                    // per-warp transpose scratch [4][32][33]
-  const uint32_t sBias = sTr + 4 * 1056 * 4;                  // bias [<= 256]
+  const uint32_t sEx = sA + S * A_BYTES;                      // exchange tiles [2 groups][128][Ntot + 4] floats
+  const uint32_t sSum = (sEx + p.groups * BM * p.ex_pitch * 4 + 7u) & ~7u;  // per-warp column sums [8][2][64] (hi, lo) pairs
+  const uint32_t sTr = sSum + 8 * 128 * 8;                    // per-warp transpose scratch [8][32][33]
+  const uint32_t sBias = sTr + 8 * 1056 * 4;                  // bias [<= 256]
   const uint32_t sBar = (sBias + 1024 + 7u) & ~7u;
-  float* ex = reinterpret_cast<float*>(gen + (sEx - base));
+  float* ex_all = reinterpret_cast<float*>(gen + (sEx - base));
   float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (sBar - base) + 8 * (2 * S + 5));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
@@ -164,13 +165,18 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       __syncwarp();
     }
   } else {
-    // ===================================== epilogue (warps 2-5) =====================================
+    // ===================================== epilogue (warps 2-5 and 6-9) =====================================
+    // Two groups of four warps: group g owns accumulator buffer g and its own exchange tile, i.e. every other tile -- the
+    // TMEM -> exchange -> shifted sums -> store chain of one tile runs under that of the next (one group was latency-bound:
+    // issue slots 28 % busy, tensor pipe 16 %, ncu).
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    float* ex = ex_all + grp * (BM * p.ex_pitch);
     const int row = q * 32 + lane;                // slab pixel held by this thread (TMEM lane)
     const bool do_stats = d.flags & MSG_CONV_STATS;
     const bool nchw = d.flags & MSG_CONV_OUT_NCHW_F32;
-    float2* wsum = reinterpret_cast<float2*>(gen + (sSum - base)) + q * 128;  // [2][64], fp64 above the 32-row partials
-    float* tr = reinterpret_cast<float*>(gen + (sTr - base)) + q * 1056;      // [32][33]
+    float2* wsum = reinterpret_cast<float2*>(gen + (sSum - base)) + (grp * 4 + q) * 128;  // [2][64], fp64 above the 32-row partials
+    float* tr = reinterpret_cast<float*>(gen + (sTr - base)) + (grp * 4 + q) * 1056;      // [32][33]
     for (int i = lane; i < 128; i += 32) wsum[i] = make_float2(0.f, 0.f);
     __syncwarp();
     int stat_img = -1;
@@ -186,14 +192,15 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       __syncwarp();
     };
     uint32_t lt = 0;
-    for (int t = t_begin; t < t_end; ++t, ++lt) {
+    const int G = p.groups;
+    for (int t = t_begin + (G == 2 ? grp : 0); t < t_end && grp < G; t += G, ++lt) {
       const int seg = t % p.segs, ny = t / p.segs;
       const int yrow = (ny % Hy) * R, img = ny / Hy;
-      const int buf = lt & 1;
+      const int buf = G == 2 ? grp : (int)(lt & 1);
       const int xcol = seg * p.Wv + row;                      // output column of this thread (if row < Wv)
       const bool col_ok = row < p.Wv && xcol < d.W;
       if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
-      mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+      mbar_wait(tfull_bar(buf), G == 2 ? (lt & 1) : ((lt >> 1) & 1));
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * d.Ntot) + ((uint32_t)(q * 32) << 16);
       // ---- phase 1: every accumulator column of this thread's slab pixel -> exchange tile (float4 stores;
@@ -214,7 +221,7 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (c0 + 4 * i < d.Ntot)
             *reinterpret_cast<float4*>(exrow + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       // ---- phase 2: out[x][c] = sum_terms ex[x + shift][col + c], then bias / stats / activation / store
       for (int g = 0; g < d.n_groups; ++g) {
         const int oc = d.grp_out_cols[g];                     // <= 16
@@ -291,9 +298,9 @@ conv_shift_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // exchange tile free for the next tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");          // exchange tile free for the next tile
     }
-    if (do_stats) flush_stats();
+    if (do_stats && grp < G) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -350,7 +357,10 @@ extern "C" int msg_conv_shift(const msg_shift_desc* d, const void* x, const void
                 "conv_shift: group %d reads past the TMEM allocation", g);
   p.ex_pitch = ((d->Ntot + 3) / 4) * 4 + 4;      // 16-byte aligned rows, pitch % 32 floats == 4: conflict-free float4 access
   if (p.ex_pitch % 32 != 4) p.ex_pitch += (4 - p.ex_pitch % 32 + 32) % 32;
-  const int fixed = p.b_bytes + BM * p.ex_pitch * 4 + 8 + 4 * 128 * 8 + 4 * 1056 * 4 + 1024 + 256 + 1024;
+  // two epilogue groups (each with its own exchange tile) when that still leaves a slab ring of >= 4 stages
+  auto fixed_for = [&](int groups) { return p.b_bytes + groups * BM * p.ex_pitch * 4 + 8 + 8 * 128 * 8 + 8 * 1056 * 4 + 1024 + 256 + 1024; };
+  p.groups = (220 * 1024 - fixed_for(2)) / A_BYTES >= 4 ? 2 : 1;
+  const int fixed = fixed_for(p.groups);
   int stages = (220 * 1024 - fixed) / A_BYTES;
   if (stages > 8) stages = 8;
   MSG_REQUIRE(stages >= 2, MSG_ERR_UNSUPPORTED, "conv_shift: not enough shared memory for the slab ring");
