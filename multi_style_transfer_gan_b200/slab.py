@@ -264,26 +264,31 @@ class ShiftProgram:
 
 def conv7_out_shift_program(c, tile_rows=2):
     """7x7 c->3 conv: per filter row ONE N=32 MMA (7 taps x 4 padded filters); 28*c/64 MMAs per output row.
-    tile_rows = 2: a tile is two output rows; input row y+dy (dy = -3..4) is loaded ONCE and feeds filter row dy+3 of
-    output row y (accumulator columns [0,32)) and filter row dy+2 of row y+1 (columns [32,64)): 8 slabs per 2 rows
-    instead of 14 -- the kernel is bound by L2 -> SM slab bytes."""
+    tile_rows = R: a tile is R output rows; input row y+dy (dy = -3..R+2) is loaded ONCE and feeds filter row dy+3-r of output
+    row y+r (accumulator columns [32r, 32r+32)) for every r it reaches: R+6 slabs per R rows instead of 7R -- the kernel is
+    bound by L2 -> SM slab bytes (ncu: ~24 B/clk/SM of TMA traffic, tensor pipe 16 %).  R = 2: 8 slabs per 2 rows (0.40 ms per
+    16 images at 512^2 with two epilogue groups); R = 4: 10 slabs per 4 rows, but its 68 KB exchange tile leaves room for one
+    epilogue group only and measures SLOWER (0.43 ms): the shifted-sum epilogue, not the slab traffic, sets the pace."""
     CB = c // 64
     terms = [(kw, kw * 4) for kw in range(7)]
-    if tile_rows == 1 or 14 * CB > SHIFT_MAX_KBLOCKS:
+    R = tile_rows
+    while R > 1 and 7 * R * CB > SHIFT_MAX_KBLOCKS:
+        R //= 2
+    if R == 1:
         kblocks = [(kh - 3, cb, 0, 32, (kh * CB + cb) * 32) for kh in range(7) for cb in range(CB)]
         return ShiftProgram(c, 32, 3, 3, kblocks, [(0, 28, 0, 3, terms)])
     kblocks, seen = [], set()
-    for dy in range(-3, 5):
+    for dy in range(-3, R + 3):
         for cb in range(CB):
             same = 0
-            for r in (0, 1):
+            for r in range(R):
                 kh = dy + 3 - r
                 if 0 <= kh <= 6:
                     kblocks.append((dy, cb, 32 * r, 32, (kh * CB + cb) * 32, int(r not in seen), same))
                     seen.add(r)
                     same = 1
-    groups = [(0, 28, 0, 3, terms, 0), (32, 28, 0, 3, terms, 1)]
-    return ShiftProgram(c, 64, 3, 3, kblocks, groups, tile_rows=2)
+    groups = [(32 * r, 28, 0, 3, terms, r) for r in range(R)]
+    return ShiftProgram(c, 32 * R, 3, 3, kblocks, groups, tile_rows=R)
 
 
 def conv7_out_shift_weights(prog, w, dtype=torch.bfloat16):

@@ -116,7 +116,7 @@ def test_conv7_input_program_pixel_pair():
     assert torch.allclose(y.permute(0, 3, 1, 2), F.conv2d(x, w, padding=3).double(), atol=1e-3, rtol=1e-4)
 
 
-@pytest.mark.parametrize("c,H,rows", [(64, 8, 2), (64, 7, 2), (128, 5, 2), (64, 6, 1)])
+@pytest.mark.parametrize("c,H,rows", [(64, 8, 2), (64, 7, 2), (128, 5, 2), (64, 6, 1), (64, 8, 4), (64, 10, 4), (64, 5, 4)])
 def test_conv7_output_shift_program(c, H, rows):
     slab = _slab_mod()
     torch.manual_seed(5)
@@ -126,7 +126,7 @@ def test_conv7_output_shift_program(c, H, rows):
     prog = slab.conv7_out_shift_program(c, tile_rows=rows)
     assert prog.tile_rows == rows
     slabs_per_tile = sum(1 for kb in prog.kblocks if not (len(kb) == 7 and kb[6]))
-    assert slabs_per_tile == (8 if rows == 2 else 7) * (c // 64)          # 8 slab loads per 2 rows instead of 14
+    assert slabs_per_tile == (rows + 6) * (c // 64)          # rows + 6 slab loads per `rows` output rows instead of 7 * rows
     y = emulate_shift(prog, nhwc(x), slab.conv7_out_shift_weights(prog, w, dtype=torch.float32))
     assert torch.allclose(y.permute(0, 3, 1, 2), F.conv2d(x, w, padding=3).double(), atol=1e-3, rtol=1e-4)
 
