@@ -79,6 +79,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     mt_begin = (int)((long long)split * p.m_tiles / p.splits);
     mt_end = (int)((long long)(split + 1) * p.m_tiles / p.splits);
   }
+  // co tiles with <= 64 channels load ONE 64-channel dy box; the second M block of the A operand aliases it (LBO = 0): rows
+  // 64-127 of the accumulator repeat rows 0-63 and are never written -- 16 KB less L2 -> SM traffic per k-block (the MSB branch,
+  // 7x7 and 128 -> 64 transposed-conv gradients were bound by it)
+  const int ndy = (d.Cout - cot * 128) <= 64 ? 1 : 2;
   const int stage_bytes = p.slab ? 2 * TILE + p.gmax * p.slab_bytes : (2 + MAXP) * TILE;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,11 +128,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         const int s = it % S;
         if (it >= (uint32_t)S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
         const uint32_t st = base + s * stage_bytes;
-        mbar_expect_tx(full_bar(s), p.slab ? (uint32_t)(2 * TILE + ng * p.slab_rows * 128) : (uint32_t)((2 + npair) * TILE));
+        mbar_expect_tx(full_bar(s), p.slab ? (uint32_t)(ndy * TILE + ng * p.slab_rows * 128) : (uint32_t)((ndy + npair) * TILE));
         // dy: two 64-channel boxes of this co tile (channels >= Cout are out of bounds -> zeros)
         const int oy = i0 * d.out_stride + d.out_off_h, ox = j0 * d.out_stride + d.out_off_w;
         tma_load_4d(st, &mapDY, full_bar(s), cot * 128, ox, oy, img);
-        tma_load_4d(st + TILE, &mapDY, full_bar(s), cot * 128 + 64, ox, oy, img);
+        if (ndy == 2) tma_load_4d(st + TILE, &mapDY, full_bar(s), cot * 128 + 64, ox, oy, img);
         // x: one shifted / strided box per (tap, ci-block) pair
         const int w_base = j0 * d.in_stride - d.pad_w, h_base = i0 * d.in_stride - d.pad_h;
         if (p.slab) {
@@ -154,7 +158,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     const bool leader = elect_one();           // one election for the whole kernel (a commit only tracks its own thread's MMAs)
     // slab mode: tile-invariant operand words
     const uint32_t mn_hi = (uint32_t)(make_mn_sw128_desc(0, 0) >> 32);
-    const uint32_t a_lbo = (uint32_t)(TILE >> 4) << 16, b_lbo = (uint32_t)((d.dil * 128) >> 4) << 16;
+    const uint32_t a_lbo = ndy == 2 ? (uint32_t)(TILE >> 4) << 16 : 0u, b_lbo = (uint32_t)((d.dil * 128) >> 4) << 16;
     const uint32_t slab_u = (uint32_t)p.slab_bytes >> 4, tap4_u = (uint32_t)(4 * d.dil * 128) >> 4;
     const int kw_first = d.KW < 4 ? d.KW : 4, kw_rest = d.KW - kw_first;
     const uint32_t idesc_n0 = idesc & ~(0x3fu << 17);
@@ -171,7 +175,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       mbar_wait(full_bar(s), (it / S) & 1);
       tc_fence_after();
       const uint32_t st = base + s * stage_bytes;
-      const uint64_t da = make_mn_sw128_desc(st, TILE);
+      const uint64_t da = make_mn_sw128_desc(st, ndy == 2 ? TILE : 0);
       const uint64_t db = make_mn_sw128_desc(st + 2 * TILE, TILE);
       if (p.slab) {
         if (leader) {
