@@ -268,6 +268,20 @@ int msg_blend_outputs(const float* const* ys, const float* w, int S, const float
                       float gain, int do_clip, float clip_lo, float clip_hi, long long numel,
                       float* out_f32, uint8_t* out_u8, void* stream);
 
+/* MultiScaleBlock branches at C = 64 (enhanced_generator.py:52-71: 1x1 | 3x3 dil 1 | 3x3 dil 2 | 3x3 dil 4, 64 -> 4 x 16
+ * channels written as ONE 64-channel slice, bias added, optional IN statistics) as a row ring of tensor-memory accumulators:
+ * every input row slab is loaded once and the three vertical taps of a dilated branch are one N = 48 MMA (csrc/msb_ring.cu).
+ * x [N,H,W,Ci_total] bf16 (channels [ci_off, ci_off+64)), w_stacks bf16 [448][64] (slab.msb64_ring_weights), bias fp32 [64] or
+ * NULL, y [N,H,W,Co_total] bf16 (channels [co_off, co_off+64)), stats fp64 [N][Co_total][2] with MSG_CONV_STATS. */
+typedef struct {
+  int dtype;                 /* MSG_BF16 */
+  int N, H, W;
+  int Ci_total, ci_off, Co_total, co_off;
+  unsigned flags;            /* MSG_CONV_STATS */
+} msg_msb_ring_desc;
+int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const void* w_stacks, const float* bias, void* y,
+                   double* stats, void* stream);
+
 /* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
  * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):
  * out fp32 NCHW [N,3,H,W] = (v / 255 - 0.5) / 0.5.  canvas (optional, may be NULL): the pasted uint8 canvas [N,H,W,3].

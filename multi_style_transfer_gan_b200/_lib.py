@@ -56,6 +56,11 @@ class ShiftDesc(ctypes.Structure):
         ("tile_rows", c_int), ("kb_same_slab", c_int * SHIFT_MAX_KBLOCKS), ("grp_row", c_int * SHIFT_MAX_GROUPS)]
 
 
+class MsbRingDesc(ctypes.Structure):
+    """mirrors msg_msb_ring_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Ci_total", "ci_off", "Co_total", "co_off")] + [("flags", c_uint)]
+
+
 SN_MAX_BATCH = 8
 
 
@@ -93,6 +98,7 @@ SIGNATURES = {
                           c_int, c_float, c_float, c_ll, _P, _P, _P],
     "msg_mse_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P],
     "msg_l1_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P, _P],
+    "msg_msb64_ring": [ctypes.POINTER(MsbRingDesc), _P, _P, _P, _P, _P, _P],
     "msg_u8_canvas_to_nchw": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_u8_strength_blend": [_P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],

@@ -102,6 +102,10 @@ class GeneratorEngine:
                             if self.inwidth[s] % 64 == 0 and self.width[s] % 16 == 0}
         self.convT_slab = os.environ.get("MSG_CONVT_SLAB", "1") == "1"
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
+        # Row-ring kernel for the C = 64 branches (csrc/msb_ring.cu): correct and tested, but NOT faster yet -- its MMA phase alone
+        # runs in 0.41 ms per 16 images at 512^2 (per-tap slab kernel: 0.67 ms in total), but the drain of a finished row does not
+        # overlap the MMAs of the next rows (0.73 ms without / 0.81 ms with IN statistics; profiles/r2_msb_ring.md).  Off by default.
+        self.msb64_ring = os.environ.get("MSG_MSB64_RING", "0") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
@@ -217,7 +221,11 @@ class GeneratorEngine:
             wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
             bn_ = [f"{s}.4.branch{i}.0.bias" for i in range(1, 5)]
             bsl = self._slab_cached(P, (s, "msb_b"), bn_, lambda: torch.cat([P[k].detach() for k in bn_]).contiguous())
-            if C == 64 and self.msb64_taps_as_n:   # taps-as-N (conv_shift.cu): 1.09 ms vs 0.89 ms per 16 images at
+            if C == 64 and self.msb64_ring:
+                # row ring of TMEM accumulators (csrc/msb_ring.cu): every input row loaded once, vertical taps stacked along N
+                wsl = self._slab_cached(P, (s, "msb_ring_w"), wn, lambda: slab.msb64_ring_weights([P[k].detach() for k in wn]))
+                slab.msb64_ring(a1, wsl, bsl, out=b, stats=stb)
+            elif C == 64 and self.msb64_taps_as_n:   # taps-as-N (conv_shift.cu): 1.09 ms vs 0.89 ms per 16 images at
                 # 512^2 for the per-tap slab kernel once its issue loop went lean, so off by default
                 wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb64_shift_weights([P[k].detach() for k in wn]))
                 slab.conv_shift(self._msb64_prog, a1, wsl, bsl, out=b, stats=stb)

@@ -347,3 +347,91 @@ def conv_shift(prog, x, w_rows, bias, out=None, co_off=0, stats=None, act=ops.AC
     _lib.call("msg_conv_shift", ctypes.byref(d), ops._p(x), ops._p(w_rows), ops._p(bias), ops._p(y), ops._p(stats),
               ops._stream())
     return nchw_out if nchw_out is not None else out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MultiScaleBlock branches at C = 64 as a ROW RING (csrc/msb_ring.cu)
+#
+# The per-tap slab kernel issues 25 MMAs of N = 16 per K step and output row, each ~40 cycles whatever N (the A operand
+# read from shared memory bounds a small-N tcgen05.mma): shared-memory bound at 15-25 % of the tensor pipe, and it loads
+# 7 input row slabs per output row.  Here a CTA walks DOWN a 128-pixel column strip: every input row is loaded ONCE, and
+# for a horizontal shift sx the three vertical taps of a dilated 3x3 branch -- which send input row r to output rows
+# r - d, r, r + d -- are ONE MMA of N = 48, because the accumulators of those three output rows sit in adjacent tensor
+# memory columns: each branch keeps a ring of row accumulators per residue class (row mod d).  10 MMAs per K step and
+# row instead of 25.  Finished rows are drained and their slots zeroed by the epilogue warps, so every MMA accumulates.
+# The functions below ARE the schedule (the CUDA kernel restates them; tests/test_msb_ring_cpu.py runs them on tensors).
+# ---------------------------------------------------------------------------------------------------------------------
+RING_DIL = (0, 1, 2, 4)            # branch 1 (1x1) has no vertical extent
+RING_SLOTS = (2, 5, 4, 4)          # ring length per residue class of branch 1..4
+RING_BASE = (0, 32, 112, 240)      # first TMEM column of each branch: 2*16 | 5*16 | 2*4*16 | 4*4*16 = 496 columns
+
+
+def ring_col(b, y):
+    """TMEM column of the 16-column accumulator of output row y of branch b."""
+    d = max(1, RING_DIL[b])
+    R = RING_SLOTS[b]
+    return RING_BASE[b] + ((y % d) * R + (y // d) % R) * 16
+
+
+def ring_row_mmas(r, y0, y1):
+    """MMAs of input row r for a strip segment of output rows [y0, y1): a list of (branch, sx, first_entry, n_entries, col)
+    -- the MMA multiplies the slab view shifted by sx with rows [16 * first_entry, 16 * (first_entry + n_entries)) of the
+    branch's weight stack for that sx (entries ordered by output row: r - d (ky = 2), r (ky = 1), r + d (ky = 0)) and
+    accumulates into n_entries * 16 columns starting at col.  Entries are merged while their ring slots are adjacent."""
+    out = []
+    if y0 <= r < y1:
+        out.append((0, 0, 0, 1, ring_col(0, r)))
+    for b in (1, 2, 3):
+        d = RING_DIL[b]
+        rows = [r - d, r, r + d]
+        run = []                                    # (entry, column)
+        runs = []
+        for e, y in enumerate(rows):
+            if not (y0 <= y < y1):
+                if run:
+                    runs.append(run)
+                run = []
+                continue
+            c = ring_col(b, y)
+            if run and c == run[-1][1] + 16:
+                run.append((e, c))
+            else:
+                if run:
+                    runs.append(run)
+                run = [(e, c)]
+        if run:
+            runs.append(run)
+        for sx in (-d, 0, d):
+            for rn in runs:
+                out.append((b, sx, rn[0][0], len(rn), rn[0][1]))
+    return out
+
+
+def msb64_ring_weights(weights, dtype=torch.bfloat16):
+    """weights: [w1 [16,64,1,1], w2..w4 [16,64,3,3]] fp32 -> [448, 64]: rows [0,16) = branch 1, then for b = 2..4 and kx = 0..2 the
+    48-row stack [ky = 2 | ky = 1 | ky = 0] (the order of the output rows r - d, r, r + d an input row feeds)."""
+    rows = [weights[0][:, :, 0, 0]]
+    for b in (1, 2, 3):
+        for kx in range(3):
+            rows += [weights[b][:, :, ky, kx] for ky in (2, 1, 0)]
+    return torch.cat(rows, 0).to(dtype).contiguous()
+
+
+def ring_stack_row(b, sx):
+    """first row of the weight stack of (branch b >= 1, horizontal shift sx) in msb64_ring_weights"""
+    d = RING_DIL[b]
+    return 16 + ((b - 1) * 3 + (sx // d + 1)) * 48
+
+
+def msb64_ring(x, w_stacks, bias, out=None, co_off=0, stats=None, ci_off=0):
+    """The four MultiScaleBlock branches at C = 64 on the row-ring kernel: x [N,H,W,>=64] bf16 -> out [N,H,W,Co_total] bf16
+    (64 channels at co_off), IN statistics accumulated into stats."""
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    if out is None:
+        out = torch.empty((N, H, W, 64), device=x.device, dtype=torch.bfloat16)
+    d = _lib.MsbRingDesc()
+    d.dtype, d.N, d.H, d.W, d.Ci_total, d.ci_off, d.Co_total, d.co_off = _lib.BF16, N, H, W, Ci_total, ci_off, out.shape[3], co_off
+    d.flags = _lib.CONV_STATS if stats is not None else 0
+    _lib.call("msg_msb64_ring", ctypes.byref(d), ops._p(x), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats), ops._stream())
+    return out

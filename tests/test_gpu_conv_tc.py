@@ -293,3 +293,27 @@ def test_slab_msb_dgrad(C, H, W):
     prog = slab.msb_dgrad_program(C)
     got = slab.conv_slab(prog, nhwc(db.float()), slab.msb_dgrad_weight_slab(prog, ws), None)
     assert_parity(nchw(got), x.grad, 1e-2, "fused MSB dgrad")
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 16, 128), (2, 40, 64), (1, 9, 20), (3, 33, 200), (2, 64, 256), (1, 130, 136)])
+def test_msb64_ring_matches_the_four_branch_convs(N, H, W):
+    """csrc/msb_ring.cu (row ring of TMEM accumulators, vertical taps stacked along N) vs the four MultiScaleBlock branch
+    convolutions of the reference (enhanced_generator.py:52-71) on bf16-rounded operands, with the IN statistics of its epilogue;
+    planes with partial strips, segments shorter than the dilation halo and several strip segments per image."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(N * 1000 + H + W)
+    x = torch.randn(N, 64, H, W, device=DEV).bfloat16().float()
+    ws = [(torch.randn(16, 64, k, k, device=DEV) * (2.0 / (64 * k * k)) ** 0.5).bfloat16().float() for k in (1, 3, 3, 3)]
+    bias = torch.randn(64, device=DEV) * 0.1
+    ref = torch.cat([F.conv2d(x, w, bias[16 * i:16 * i + 16], padding=(w.shape[2] // 2) * d, dilation=d)
+                     for i, (w, d) in enumerate(zip(ws, (1, 1, 2, 4)))], 1)
+    st = ops.new_stats(N, 64, DEV)
+    out = slab.msb64_ring(nhwc(x).bfloat16(), slab.msb64_ring_weights(ws), bias, stats=st)
+    torch.cuda.synchronize()
+    assert_parity(out.float().permute(0, 3, 1, 2), ref, 1e-2, f"msb64 ring {N}x{H}x{W}")
+    # statistics of the fp32 accumulators (before the bf16 rounding of the store)
+    assert_parity(st[..., 0].float(), ref.sum(dim=(2, 3)), 2e-3, "ring sum", floor=1e-2)
+    assert_parity(st[..., 1].float(), (ref * ref).sum(dim=(2, 3)), 2e-3, "ring sum of squares")
+    # a second launch gives the same bits (the ring is zeroed and drained deterministically)
+    out2 = slab.msb64_ring(nhwc(x).bfloat16(), slab.msb64_ring_weights(ws), bias)
+    assert torch.equal(out, out2)

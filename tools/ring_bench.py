@@ -1,0 +1,41 @@
+"""Times the C = 64 MultiScaleBlock branch kernels on the bench geometry (16 x 512 x 512 x 64 bf16): the row-ring kernel with /
+without IN statistics, and the per-tap row-slab kernel.  Usage: python tools/ring_bench.py [N H W]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multi_style_transfer_gan_b200 import ops, slab  # noqa: E402
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    N, H, W = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (16, 512, 512)
+    torch.manual_seed(0)
+    x = torch.randn(N, H, W, 64, device="cuda").bfloat16()
+    ws = [torch.randn(16, 64, k, k, device="cuda") * 0.05 for k in (1, 3, 3, 3)]
+    bias = torch.randn(64, device="cuda") * 0.1
+    out = torch.empty_like(x)
+    st = ops.new_stats(N, 64, "cuda")
+    wr = slab.msb64_ring_weights(ws)
+    print(f"ring, stats    : {timed(lambda: slab.msb64_ring(x, wr, bias, out=out, stats=st)):.4f} ms")
+    print(f"ring, no stats : {timed(lambda: slab.msb64_ring(x, wr, bias, out=out)):.4f} ms")
+    prog = slab.msb_program(64)
+    wsl = slab.msb_weight_slab(prog, ws)
+    print(f"per-tap slab   : {timed(lambda: slab.conv_slab(prog, x, wsl, bias, out=out, stats=st)):.4f} ms")
+
+
+if __name__ == "__main__":
+    main()
