@@ -61,7 +61,8 @@ __device__ __forceinline__ uint32_t ring_col(int b, int y) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const RingParams p) {
+msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapY, const RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
@@ -72,7 +73,8 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const uint32_t sSum = sA + S * SLAB_BYTES;              // per-warp running column sums [16 warps][2][16] (hi, lo) pairs
   const uint32_t sTr = sSum + 16 * 32 * 8;                // per-warp transpose scratch [16][16][33] floats
   const uint32_t sBias = sTr + 16 * 528 * 4;              // bias [64]
-  const uint32_t sBar = (sBias + 256 + 7u) & ~7u;
+  const uint32_t sOut = (sBias + 256 + 127u) & ~127u;     // per-warp output staging [16 warps][2][32 px][32 B]
+  const uint32_t sBar = (sOut + 16 * 2 * 1024 + 7u) & ~7u;
   float* sbias = reinterpret_cast<float*>(gen + (sBias - base));
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
@@ -95,6 +97,7 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapY)) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -246,7 +249,7 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     float bia[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) bia[c] = sbias[16 * b + c];
-    uint32_t k = 0;
+    uint32_t k = 0, nst = 0;               // steps, pieces stored by this warp
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
       int img, seg, y0, y1;
       item(t, img, seg, y0, y1);
@@ -268,18 +271,33 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           float v[16];
           tmem_ld16(taddr, v);
           tmem_ld_wait();
-#if !defined(RING_EXP) || RING_EXP != 5
+#if !defined(RING_EXP) || (RING_EXP != 5 && RING_EXP != 6 && RING_EXP != 7)
           tmem_st16(taddr, zero16);                                  // the slot is free for the row that wraps onto it
 #endif
 #pragma unroll
           for (int c = 0; c < 16; ++c) v[c] += bia[c];
-          if (valid) {
-            __nv_bfloat16* dst = p.y + (((size_t)img * p.H + y) * p.W + xcol) * p.Co_total + p.co_off + 16 * b;
+          {
+            // the warp's [32 pixels x 16 channels] piece: 32 bytes per thread into its staging buffer, then ONE TMA store (the tensor
+            // map clips pixels beyond the plane).  Per-thread global stores -- 32 scattered sectors per warp instruction, each 128-byte
+            // line assembled from four branches at four different times -- held the whole kernel back: 0.73 ms with two 16-byte
+            // stores per thread, 0.63 with one 32-byte store, MMA-bound (0.42) without stores.
             float lo[8], hi8[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) { lo[c] = v[c]; hi8[c] = v[8 + c]; }
-            *reinterpret_cast<uint4*>(dst) = pack8(lo);
-            *reinterpret_cast<uint4*>(dst + 8) = pack8(hi8);
+            uint8_t* stg = gen + (sOut - base) + ((warp - EPI0) * 2 + (int)(nst & 1)) * 1024;
+            if (nst >= 2) {                                          // the store issued two pieces ago has read this buffer
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+            *reinterpret_cast<uint4*>(stg + lane * 32) = pack8(lo);
+            *reinterpret_cast<uint4*>(stg + lane * 32 + 16) = pack8(hi8);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&mapY, smem_u32(stg), p.co_off + 16 * b, seg * BM + q * 32, y, img);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nst;
           }
           tmem_st_wait();
           tc_fence_before();
@@ -310,6 +328,7 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
     if (do_stats) flush_stats();
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -357,13 +376,22 @@ extern "C" int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const v
   const long long total = (long long)d->N * p.segs * p.n_vseg;
   MSG_REQUIRE(total < 0x7fffffffLL, MSG_ERR_SHAPE, "msb64_ring: too many strips");
   p.total_items = (int)total;
-  const int fixed = W_BYTES + 16 * 32 * 8 + 16 * 528 * 4 + 256 + 8 + 512 + 1024;
+  const int fixed = W_BYTES + 16 * 32 * 8 + 16 * 528 * 4 + 256 + 128 + 16 * 2 * 1024 + 8 + 512 + 1024;
   int stages = (220 * 1024 - fixed) / SLAB_BYTES;
   if (stages > 8) stages = 8;
   p.stages = stages;
   const size_t smem = (size_t)stages * SLAB_BYTES + fixed;
 
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapY;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Co_total, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->Co_total * 2, (cuuint64_t)d->W * d->Co_total * 2, (cuuint64_t)d->H * d->W * d->Co_total * 2};
+    cuuint32_t box[4] = {16, 32, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSG_REQUIRE(r == CUDA_SUCCESS, MSG_ERR_CUDA, "msb64_ring: cuTensorMapEncodeTiled(y) failed with %d", (int)r);
+  }
   {
     cuuint64_t dims[4] = {64, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->Ci_total * 2, (cuuint64_t)d->W * d->Ci_total * 2, (cuuint64_t)d->H * d->W * d->Ci_total * 2};
@@ -391,6 +419,6 @@ extern "C" int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const v
   }
   int grid = sms;
   if (grid > p.total_items) grid = p.total_items;
-  msb64_ring_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(mapA, mapB, p);
+  msb64_ring_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(mapA, mapB, mapY, p);
   return check_launch("msb64_ring_kernel");
 }

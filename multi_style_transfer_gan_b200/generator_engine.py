@@ -102,10 +102,9 @@ class GeneratorEngine:
                             if self.inwidth[s] % 64 == 0 and self.width[s] % 16 == 0}
         self.convT_slab = os.environ.get("MSG_CONVT_SLAB", "1") == "1"
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
-        # Row-ring kernel for the C = 64 branches (csrc/msb_ring.cu): correct and tested, but NOT faster yet -- its MMA phase alone
-        # runs in 0.41 ms per 16 images at 512^2 (per-tap slab kernel: 0.67 ms in total), but the drain of a finished row does not
-        # overlap the MMAs of the next rows (0.73 ms without / 0.81 ms with IN statistics; profiles/r2_msb_ring.md).  Off by default.
-        self.msb64_ring = os.environ.get("MSG_MSB64_RING", "0") == "1"
+        # Row-ring kernel for the C = 64 branches (csrc/msb_ring.cu): 0.48 ms per 16 images at 512^2 vs 0.67 ms for the per-tap slab
+        # kernel (profiles/r2_msb_ring.md).  MSG_MSB64_RING=0 falls back to the latter.
+        self.msb64_ring = os.environ.get("MSG_MSB64_RING", "1") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
