@@ -43,7 +43,8 @@ constexpr int NTHREADS = 32 * (EPI0 + 16);      // TMA, 3 MMA issuers, 4 x 4 epi
 
 struct RingParams {
   int N, H, W, Co_total, co_off;
-  int segs, seg_rows, n_vseg, total_items;
+  int segs;
+  long long total_rows;           // N * segs * H
   int stages;
   const float* bias;
   __nv_bfloat16* y;
@@ -115,14 +116,17 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   tc_fence_after();
 
-  auto item = [&](int t, int& img, int& seg, int& y0, int& y1) {
-    const int per_img = p.n_vseg * p.segs;
-    img = t / per_img;
-    const int rem = t - img * per_img;
-    const int vs = rem / p.segs;
-    seg = rem - vs * p.segs;
-    y0 = vs * p.seg_rows;
-    y1 = y0 + p.seg_rows < p.H ? y0 + p.seg_rows : p.H;
+  // Work = the rows of all column strips laid end to end (strip = (image, 128-pixel segment), H rows each); CTA i takes the i-th
+  // equal share of that range, i.e. at most a few pieces of consecutive strips: every SM gets the same number of rows (whole-strip
+  // segments left 20 of 148 SMs idle at 16 x 512 x 512) and a piece re-reads only its 8 halo rows.
+  const long long g_lo = (long long)blockIdx.x * p.total_rows / gridDim.x, g_hi = (long long)(blockIdx.x + 1) * p.total_rows / gridDim.x;
+  auto item = [&](long long g, int& img, int& seg, int& y0, int& y1) {
+    const int strip = (int)(g / p.H);
+    y0 = (int)(g - (long long)strip * p.H);
+    const long long left = g_hi - g;
+    y1 = (long long)(p.H - y0) < left ? p.H : y0 + (int)left;
+    img = strip / p.segs;
+    seg = strip - img * p.segs;
   };
 
   if (warp == 0) {
@@ -132,9 +136,10 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int r = 0; r < W_ROWS; r += 64) tma_load_2d(sB + r * 128, &mapB, wres_bar, 0, r);
       int s = 0;
       uint32_t n = 0;                      // slabs issued
-      for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+      for (long long g = g_lo; g < g_hi;) {
         int img, seg, y0, y1;
-        item(t, img, seg, y0, y1);
+        item(g, img, seg, y0, y1);
+        g += y1 - y0;
         const int r_lo = y0 - HALO < 0 ? 0 : y0 - HALO, r_hi = y1 + HALO > p.H ? p.H : y1 + HALO;
         for (int r = r_lo; r < r_hi; ++r, ++n) {
           if (n >= (uint32_t)S) mbar_wait(empty_bar(s), ((n / S) - 1) & 1);
@@ -154,9 +159,10 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     int s = 0;
     uint32_t n = 0, k = 0;                 // slabs consumed, global step count
     mbar_wait(wres_bar, 0);
-    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+    for (long long g = g_lo; g < g_hi;) {
       int img, seg, y0, y1;
-      item(t, img, seg, y0, y1);
+      item(g, img, seg, y0, y1);
+      g += y1 - y0;
       for (int r = y0 - HALO; r < y1 + HALO; ++r, ++k) {
         // the epilogue must have drained (and zeroed) everything up to step k - 2: the slot this row first touches in the
         // two-slot ring of the 1x1 branch belonged to output row r - 2 (the other rings have more slack, slab.py)
@@ -250,9 +256,10 @@ msb64_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
     for (int c = 0; c < 16; ++c) bia[c] = sbias[16 * b + c];
     uint32_t k = 0, nst = 0;               // steps, pieces stored by this warp
-    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+    for (long long g = g_lo; g < g_hi;) {
       int img, seg, y0, y1;
-      item(t, img, seg, y0, y1);
+      item(g, img, seg, y0, y1);
+      g += y1 - y0;
       const int xcol = seg * BM + row;
       const bool valid = xcol < p.W;
       if (do_stats && img != stat_img) { flush_stats(); stat_img = img; }
@@ -359,23 +366,9 @@ extern "C" int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const v
   p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y); p.stats = (d->flags & MSG_CONV_STATS) ? stats : nullptr;
   MSG_REQUIRE(!(d->flags & MSG_CONV_STATS) || stats != nullptr, MSG_ERR_SHAPE, "msb64_ring: stats buffer missing");
   p.segs = (d->W + BM - 1) / BM;
-  // rows per strip segment: a segment re-reads 8 halo rows, and the items should fill whole waves of CTAs
   const int sms = sm_count();
-  int best_s = d->H;
-  long long best_cost = -1;
-  const int cands[] = {16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 1024};
-  for (int s : cands) {
-    const int S = s < d->H ? s : d->H;
-    const long long items = (long long)d->N * p.segs * ((d->H + S - 1) / S);
-    const long long waves = (items + sms - 1) / sms;
-    const long long cost = waves * (S + 2 * HALO);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = S; }
-  }
-  p.seg_rows = best_s;
-  p.n_vseg = (d->H + p.seg_rows - 1) / p.seg_rows;
-  const long long total = (long long)d->N * p.segs * p.n_vseg;
-  MSG_REQUIRE(total < 0x7fffffffLL, MSG_ERR_SHAPE, "msb64_ring: too many strips");
-  p.total_items = (int)total;
+  p.total_rows = (long long)d->N * p.segs * d->H;
+  MSG_REQUIRE(p.total_rows < (1LL << 40), MSG_ERR_SHAPE, "msb64_ring: too many rows");
   const int fixed = W_BYTES + 16 * 32 * 8 + 16 * 528 * 4 + 256 + 128 + 16 * 2 * 1024 + 8 + 512 + 1024;
   int stages = (220 * 1024 - fixed) / SLAB_BYTES;
   if (stages > 8) stages = 8;
@@ -417,8 +410,8 @@ extern "C" int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const v
     MSG_REQUIRE(e == cudaSuccess, MSG_ERR_CUDA, "msb64_ring: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set.done();
   }
-  int grid = sms;
-  if (grid > p.total_items) grid = p.total_items;
+  long long grid_ll = p.total_rows / 8;       // at least 8 rows per CTA (each piece re-reads 8 halo rows)
+  int grid = grid_ll < 1 ? 1 : (grid_ll > sms ? sms : (int)grid_ll);
   msb64_ring_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(mapA, mapB, mapY, p);
   return check_launch("msb64_ring_kernel");
 }
