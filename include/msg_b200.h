@@ -281,6 +281,12 @@ typedef struct {
 } msg_msb_ring_desc;
 int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const void* w_stacks, const float* bias, void* y,
                    double* stats, void* stream);
+/* The same for C = 64 or C = 128 input / output channels.  At C = 128 a row accumulator is 32 tensor-memory columns and the four
+ * rings do not fit 512 columns: branches 1 + 2, branch 3 and branch 4 run as three launches, each with its own resident weight
+ * stacks.  w_stacks: slab.msb_ring_weights(weights, C) -- per pass, per 64-channel block of the input, the stacks of the pass's
+ * branches ([448][64] at C = 64, [1792][64] at C = 128); bias fp32 [C] or NULL. */
+int msg_msb_ring(const msg_msb_ring_desc* d, int C, const void* x, const void* w_stacks, const float* bias, void* y,
+                 double* stats, void* stream);
 
 /* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
  * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):

@@ -99,6 +99,7 @@ SIGNATURES = {
     "msg_mse_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P],
     "msg_l1_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P, _P],
     "msg_msb64_ring": [ctypes.POINTER(MsbRingDesc), _P, _P, _P, _P, _P, _P],
+    "msg_msb_ring": [ctypes.POINTER(MsbRingDesc), ctypes.c_int, _P, _P, _P, _P, _P, _P],
     "msg_u8_canvas_to_nchw": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_u8_strength_blend": [_P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],

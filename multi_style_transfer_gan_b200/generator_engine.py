@@ -105,6 +105,8 @@ class GeneratorEngine:
         # Row-ring kernel for the C = 64 branches (csrc/msb_ring.cu): 0.48 ms per 16 images at 512^2 vs 0.67 ms for the per-tap slab
         # kernel (profiles/r2_msb_ring.md).  MSG_MSB64_RING=0 falls back to the latter.
         self.msb64_ring = os.environ.get("MSG_MSB64_RING", "1") == "1"
+        # ... and for the C = 128 branches (three passes): 0.27 ms vs 0.38 ms per 16 images at 256^2.  MSG_MSB128_RING=0 falls back.
+        self.msb128_ring = os.environ.get("MSG_MSB128_RING", "1") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
@@ -220,10 +222,11 @@ class GeneratorEngine:
             wn = [f"{s}.4.branch{i}.0.weight" for i in range(1, 5)]
             bn_ = [f"{s}.4.branch{i}.0.bias" for i in range(1, 5)]
             bsl = self._slab_cached(P, (s, "msb_b"), bn_, lambda: torch.cat([P[k].detach() for k in bn_]).contiguous())
-            if C == 64 and self.msb64_ring:
+            if (C == 64 and self.msb64_ring) or (C == 128 and self.msb128_ring):
                 # row ring of TMEM accumulators (csrc/msb_ring.cu): every input row loaded once, vertical taps stacked along N
-                wsl = self._slab_cached(P, (s, "msb_ring_w"), wn, lambda: slab.msb64_ring_weights([P[k].detach() for k in wn]))
-                slab.msb64_ring(a1, wsl, bsl, out=b, stats=stb)
+                # (one launch at C = 64, three passes at C = 128)
+                wsl = self._slab_cached(P, (s, "msb_ring_w"), wn, lambda: slab.msb_ring_weights([P[k].detach() for k in wn], C))
+                slab.msb_ring(a1, wsl, bsl, C, out=b, stats=stb)
             elif C == 64 and self.msb64_taps_as_n:   # taps-as-N (conv_shift.cu): 1.09 ms vs 0.89 ms per 16 images at
                 # 512^2 for the per-tap slab kernel once its issue loop went lean, so off by default
                 wsl = self._slab_cached(P, (s, "msb_w"), wn, lambda: slab.msb64_shift_weights([P[k].detach() for k in wn]))

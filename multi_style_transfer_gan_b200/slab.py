@@ -362,26 +362,52 @@ def conv_shift(prog, x, w_rows, bias, out=None, co_off=0, stats=None, act=ops.AC
 # The functions below ARE the schedule (the CUDA kernel restates them; tests/test_msb_ring_cpu.py runs them on tensors).
 # ---------------------------------------------------------------------------------------------------------------------
 RING_DIL = (0, 1, 2, 4)            # branch 1 (1x1) has no vertical extent
-RING_SLOTS = (2, 5, 4, 4)          # ring length per residue class of branch 1..4
-RING_BASE = (0, 32, 112, 240)      # first TMEM column of each branch: 2*16 | 5*16 | 2*4*16 | 4*4*16 = 496 columns
+# Ring length per residue class of each branch, per PASS (= kernel launch).  C = 64: all four branches share the 512 tensor-memory
+# columns (16 per row accumulator: 3*16 | 5*16 | 2*4*16 | 4*4*16 = 512).  C = 128 (32 columns per row accumulator) does not fit in
+# one pass: branches 1 + 2 (4*32 + 2 sets of 6*32 = 512 columns), branch 3 (2*8*32 = 512) and branch 4 (4*4*32 = 512) run as
+# three launches, each with its own resident weight stacks.
+RING_PASSES = {64: (((0, 3), (1, 5), (2, 4), (3, 4)),),
+               128: (((0, 4), (1, 6)), ((2, 8),), ((3, 4),))}
+# How many steps (input rows) the MMA issuers may run ahead of the epilogue: the slot of the row a 3x3 branch finishes at step k is
+# touched again at step k + (R - 2) d (the 1x1 branch: k + R), so the lead is at most the minimum of that over the pass.
+RING_LEAD = {64: (3,), 128: (4, 8, 8)}
 
 
-def ring_col(b, y):
-    """TMEM column of the 16-column accumulator of output row y of branch b."""
+def ring_dup(C, ps, b):
+    """accumulator sets of branch b in pass ps: the dilation-1 3x3 at C = 128 keeps one ring for even and one for odd INPUT rows (two
+    issuers share the branch without touching the same columns; the epilogue adds the sets).  The second set follows the first."""
+    return 2 if (C == 128 and ps == 0 and b == 1) else 1
+
+
+def ring_layout(C, ps=0):
+    """{branch: (ring length per residue class, first TMEM column)} of pass ps"""
+    Q, col, out = C // 4, 0, {}
+    for b, R in RING_PASSES[C][ps]:
+        out[b] = (R, col)
+        col += max(1, RING_DIL[b]) * R * Q * ring_dup(C, ps, b)
+    assert col <= 512
+    return out
+
+
+def ring_col(b, y, C=64, ps=0):
+    """TMEM column of the C/4-column accumulator of output row y of branch b."""
     d = max(1, RING_DIL[b])
-    R = RING_SLOTS[b]
-    return RING_BASE[b] + ((y % d) * R + (y // d) % R) * 16
+    R, base = ring_layout(C, ps)[b]
+    return base + ((y % d) * R + (y // d) % R) * (C // 4)
 
 
-def ring_row_mmas(r, y0, y1):
-    """MMAs of input row r for a strip segment of output rows [y0, y1): a list of (branch, sx, first_entry, n_entries, col)
-    -- the MMA multiplies the slab view shifted by sx with rows [16 * first_entry, 16 * (first_entry + n_entries)) of the
-    branch's weight stack for that sx (entries ordered by output row: r - d (ky = 2), r (ky = 1), r + d (ky = 0)) and
-    accumulates into n_entries * 16 columns starting at col.  Entries are merged while their ring slots are adjacent."""
-    out = []
-    if y0 <= r < y1:
-        out.append((0, 0, 0, 1, ring_col(0, r)))
+def ring_row_mmas(r, y0, y1, C=64, ps=0):
+    """MMAs of input row r for a strip segment of output rows [y0, y1) in pass ps: a list of (branch, sx, first_entry, n_entries,
+    col) -- the MMA multiplies the slab view shifted by sx with rows [Q * first_entry, Q * (first_entry + n_entries)) of the
+    branch's weight stack for that sx (entries ordered by output row: r - d (ky = 2), r (ky = 1), r + d (ky = 0)) and accumulates
+    into n_entries * Q columns starting at col (Q = C / 4).  Entries are merged while their ring slots are adjacent."""
+    Q, out = C // 4, []
+    lay = ring_layout(C, ps)
+    if 0 in lay and y0 <= r < y1:
+        out.append((0, 0, 0, 1, ring_col(0, r, C, ps)))
     for b in (1, 2, 3):
+        if b not in lay:
+            continue
         d = RING_DIL[b]
         rows = [r - d, r, r + d]
         run = []                                    # (entry, column)
@@ -392,8 +418,8 @@ def ring_row_mmas(r, y0, y1):
                     runs.append(run)
                 run = []
                 continue
-            c = ring_col(b, y)
-            if run and c == run[-1][1] + 16:
+            c = ring_col(b, y, C, ps)
+            if run and c == run[-1][1] + Q:
                 run.append((e, c))
             else:
                 if run:
@@ -407,31 +433,60 @@ def ring_row_mmas(r, y0, y1):
     return out
 
 
+def ring_pass_rows(C, ps):
+    """weight rows of pass ps (per 64-channel block): Q for the 1x1 branch, 9 * Q for a 3x3 branch"""
+    Q = C // 4
+    return sum(Q if b == 0 else 9 * Q for b, _ in RING_PASSES[C][ps])
+
+
+def ring_stack_row(b, sx, C=64, ps=0):
+    """first row (inside pass ps's block of one 64-channel slice) of the weight stack of (branch b >= 1, horizontal shift sx)"""
+    Q, row = C // 4, 0
+    for bb, _ in RING_PASSES[C][ps]:
+        if bb == b:
+            return row + (sx // RING_DIL[b] + 1) * 3 * Q
+        row += Q if bb == 0 else 9 * Q
+    raise KeyError(b)
+
+
+def msb_ring_weights(weights, C=64, dtype=torch.bfloat16):
+    """weights: [w1 [Q,C,1,1], w2..w4 [Q,C,3,3]] fp32 -> [sum over passes of (C/64) * rows(pass), 64]: per pass, per 64-channel block
+    kb, the rows of its branches: Q rows of the 1x1 branch, then for every 3x3 branch and kx = 0..2 the 3Q-row stack
+    [ky = 2 | ky = 1 | ky = 0] (the order of the output rows r - d, r, r + d an input row feeds)."""
+    out = []
+    for ps in range(len(RING_PASSES[C])):
+        for kb in range(C // 64):
+            sl = slice(kb * 64, (kb + 1) * 64)
+            for b, _ in RING_PASSES[C][ps]:
+                if b == 0:
+                    out.append(weights[0][:, sl, 0, 0])
+                else:
+                    for kx in range(3):
+                        out += [weights[b][:, sl, ky, kx] for ky in (2, 1, 0)]
+    return torch.cat(out, 0).to(dtype).contiguous()
+
+
 def msb64_ring_weights(weights, dtype=torch.bfloat16):
-    """weights: [w1 [16,64,1,1], w2..w4 [16,64,3,3]] fp32 -> [448, 64]: rows [0,16) = branch 1, then for b = 2..4 and kx = 0..2 the
-    48-row stack [ky = 2 | ky = 1 | ky = 0] (the order of the output rows r - d, r, r + d an input row feeds)."""
-    rows = [weights[0][:, :, 0, 0]]
-    for b in (1, 2, 3):
-        for kx in range(3):
-            rows += [weights[b][:, :, ky, kx] for ky in (2, 1, 0)]
-    return torch.cat(rows, 0).to(dtype).contiguous()
+    return msb_ring_weights(weights, 64, dtype)
 
 
-def ring_stack_row(b, sx):
-    """first row of the weight stack of (branch b >= 1, horizontal shift sx) in msb64_ring_weights"""
-    d = RING_DIL[b]
-    return 16 + ((b - 1) * 3 + (sx // d + 1)) * 48
-
-
-def msb64_ring(x, w_stacks, bias, out=None, co_off=0, stats=None, ci_off=0):
-    """The four MultiScaleBlock branches at C = 64 on the row-ring kernel: x [N,H,W,>=64] bf16 -> out [N,H,W,Co_total] bf16
-    (64 channels at co_off), IN statistics accumulated into stats."""
+def msb_ring(x, w_stacks, bias, C=64, out=None, co_off=0, stats=None, ci_off=0):
+    """The four MultiScaleBlock branches at C = 64 / 128 on the row-ring kernel: x [N,H,W,>=C] bf16 -> out [N,H,W,Co_total] bf16
+    (C channels at co_off), IN statistics accumulated into stats.  w_stacks = msb_ring_weights(weights, C)."""
     ops._dev(x)
     N, H, W, Ci_total = x.shape
     if out is None:
-        out = torch.empty((N, H, W, 64), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((N, H, W, C), device=x.device, dtype=torch.bfloat16)
+    rows = sum(ring_pass_rows(C, ps) for ps in range(len(RING_PASSES[C]))) * (C // 64)
+    if tuple(w_stacks.shape) != (rows, 64) or w_stacks.dtype != torch.bfloat16:
+        raise ValueError(f"msb_ring: w_stacks must be bf16 [{rows}, 64] (msb_ring_weights(weights, {C})), got {tuple(w_stacks.shape)}")
     d = _lib.MsbRingDesc()
     d.dtype, d.N, d.H, d.W, d.Ci_total, d.ci_off, d.Co_total, d.co_off = _lib.BF16, N, H, W, Ci_total, ci_off, out.shape[3], co_off
     d.flags = _lib.CONV_STATS if stats is not None else 0
-    _lib.call("msg_msb64_ring", ctypes.byref(d), ops._p(x), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats), ops._stream())
+    _lib.call("msg_msb_ring", ctypes.byref(d), C, ops._p(x), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats), ops._stream())
+    _lib.launches += len(RING_PASSES[C]) - 1        # one kernel per pass
     return out
+
+
+def msb64_ring(x, w_stacks, bias, out=None, co_off=0, stats=None, ci_off=0):
+    return msb_ring(x, w_stacks, bias, 64, out, co_off, stats, ci_off)

@@ -317,3 +317,29 @@ def test_msb64_ring_matches_the_four_branch_convs(N, H, W):
     # a second launch gives the same bits (the ring is zeroed and drained deterministically)
     out2 = slab.msb64_ring(nhwc(x).bfloat16(), slab.msb64_ring_weights(ws), bias)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 16, 128), (2, 40, 64), (1, 9, 20), (3, 33, 200), (2, 64, 256)])
+def test_msb128_ring_matches_the_four_branch_convs(N, H, W):
+    """the C = 128 row ring (three passes: branches 1 + 2 | 3 | 4, 32-column row accumulators, two 64-channel K blocks per slab)
+    vs the four branch convolutions (enhanced_generator.py:52-71) with the IN statistics of its epilogue, written as a 128-channel
+    slice of a wider tensor."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(N * 1000 + H + W + 7)
+    C, Q = 128, 32
+    x = torch.randn(N, C, H, W, device=DEV).bfloat16().float()
+    ws = [(torch.randn(Q, C, k, k, device=DEV) * (2.0 / (C * k * k)) ** 0.5).bfloat16().float() for k in (1, 3, 3, 3)]
+    bias = torch.randn(C, device=DEV) * 0.1
+    ref = torch.cat([F.conv2d(x, w, bias[Q * i:Q * i + Q], padding=(w.shape[2] // 2) * d, dilation=d)
+                     for i, (w, d) in enumerate(zip(ws, (1, 1, 2, 4)))], 1)
+    st = ops.new_stats(N, 2 * C, DEV)
+    out = torch.zeros(N, H, W, 2 * C, device=DEV, dtype=torch.bfloat16)
+    slab.msb_ring(nhwc(x).bfloat16(), slab.msb_ring_weights(ws, C), bias, C, out=out, co_off=C, stats=st)
+    torch.cuda.synchronize()
+    assert float(out[..., :C].abs().max()) == 0.0                          # only the slice is written
+    assert_parity(out[..., C:].float().permute(0, 3, 1, 2), ref, 1e-2, f"msb128 ring {N}x{H}x{W}")
+    assert_parity(st[:, C:, 0].float(), ref.sum(dim=(2, 3)), 2e-3, "ring sum", floor=1e-2)
+    assert_parity(st[:, C:, 1].float(), (ref * ref).sum(dim=(2, 3)), 2e-3, "ring sum of squares")
+    out2 = torch.zeros_like(out)
+    slab.msb_ring(nhwc(x).bfloat16(), slab.msb_ring_weights(ws, C), bias, C, out=out2, co_off=C)
+    assert torch.equal(out, out2)

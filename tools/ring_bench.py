@@ -21,8 +21,23 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
+def bench128(N, H, W):
+    C, Q = 128, 32
+    x = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    ws = [torch.randn(Q, C, k, k, device="cuda") * 0.05 for k in (1, 3, 3, 3)]
+    bias = torch.randn(C, device="cuda") * 0.1
+    out = torch.empty_like(x)
+    st = ops.new_stats(N, C, "cuda")
+    wr = slab.msb_ring_weights(ws, C)
+    print(f"C=128 {N}x{H}x{W} ring (3 passes), stats : {timed(lambda: slab.msb_ring(x, wr, bias, C, out=out, stats=st)):.4f} ms")
+    prog = slab.msb_program(C)
+    wsl = slab.msb_weight_slab(prog, ws)
+    print(f"C=128 per-tap slab                       : {timed(lambda: slab.conv_slab(prog, x, wsl, bias, out=out, stats=st)):.4f} ms")
+
+
 def main():
     N, H, W = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (16, 512, 512)
+    bench128(N, H // 2, W // 2)
     torch.manual_seed(0)
     x = torch.randn(N, H, W, 64, device="cuda").bfloat16()
     ws = [torch.randn(16, 64, k, k, device="cuda") * 0.05 for k in (1, 3, 3, 3)]
