@@ -288,6 +288,22 @@ int msg_msb64_ring(const msg_msb_ring_desc* d, const void* x, const void* w_stac
 int msg_msb_ring(const msg_msb_ring_desc* d, int C, const void* x, const void* w_stacks, const float* bias, void* y,
                  double* stats, void* stream);
 
+/* ConvTranspose2d(kernel 4, stride 2, padding 1) of the decoder (enhanced_generator.py:116-123) as a row ring of tensor-memory
+ * accumulators (csrc/convt_ring.cu): one launch per horizontal output phase and 64 output channels, every input row slab loaded
+ * once per launch, the four vertical taps of a horizontal tap as ONE N = 256 MMA.  Replaces the four sub-pixel phase launches of
+ * msg_conv_slab for Cin in {64, 128} (the phase's weights stay resident in shared memory).
+ * x [N,H,W,Ci_total] bf16 (channels [ci_off, ci_off+Cin)), w_stacks bf16 (slab.convt_ring_weights), bias fp32 [Cout] or NULL,
+ * y [N,2H,2W,Co_total] bf16 (channels [co_off, co_off+Cout)), stats fp64 [N][Co_total][2] with MSG_CONV_STATS. */
+typedef struct {
+  int dtype;                 /* MSG_BF16 */
+  int N, H, W;               /* input plane */
+  int Cin, Cout;
+  int Ci_total, ci_off, Co_total, co_off;
+  unsigned flags;            /* MSG_CONV_STATS */
+} msg_convt_ring_desc;
+int msg_convt_ring(const msg_convt_ring_desc* d, const void* x, const void* w_stacks, const float* bias, void* y,
+                   double* stats, void* stream);
+
 /* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
  * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):
  * out fp32 NCHW [N,3,H,W] = (v / 255 - 0.5) / 0.5.  canvas (optional, may be NULL): the pasted uint8 canvas [N,H,W,3].

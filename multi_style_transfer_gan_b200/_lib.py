@@ -61,6 +61,11 @@ class MsbRingDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Ci_total", "ci_off", "Co_total", "co_off")] + [("flags", c_uint)]
 
 
+class ConvtRingDesc(ctypes.Structure):
+    """mirrors msg_convt_ring_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Cin", "Cout", "Ci_total", "ci_off", "Co_total", "co_off")] + [("flags", c_uint)]
+
+
 SN_MAX_BATCH = 8
 
 
@@ -100,6 +105,7 @@ SIGNATURES = {
     "msg_l1_loss": [_P, _P, c_float, c_ll, c_float, _P, _P, _P, _P],
     "msg_msb64_ring": [ctypes.POINTER(MsbRingDesc), _P, _P, _P, _P, _P, _P],
     "msg_msb_ring": [ctypes.POINTER(MsbRingDesc), ctypes.c_int, _P, _P, _P, _P, _P, _P],
+    "msg_convt_ring": [ctypes.POINTER(ConvtRingDesc), _P, _P, _P, _P, _P, _P],
     "msg_u8_canvas_to_nchw": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_u8_strength_blend": [_P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],

@@ -107,6 +107,8 @@ class GeneratorEngine:
         self.msb64_ring = os.environ.get("MSG_MSB64_RING", "1") == "1"
         # ... and for the C = 128 branches (three passes): 0.27 ms vs 0.38 ms per 16 images at 256^2.  MSG_MSB128_RING=0 falls back.
         self.msb128_ring = os.environ.get("MSG_MSB128_RING", "1") == "1"
+        # ... and for the 128 -> 64 transposed conv of up2 (csrc/convt_ring.cu).  MSG_CONVT_RING=0 falls back to the phase slabs.
+        self.convT_ring = os.environ.get("MSG_CONVT_RING", "1") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
@@ -174,7 +176,15 @@ class GeneratorEngine:
         if arena is None:
             arena = _StatsArena(N, 3 * C, dev)
         st0 = arena.take(C)
-        if (self.convT_slab and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
+        if (self.convT_ring and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] in (64, 128) and C % 64 == 0):
+            # transposed conv as a row ring of TMEM accumulators (csrc/convt_ring.cu): one launch per horizontal output phase, every
+            # input row loaded once per launch, the four vertical taps of a horizontal tap as one N = 256 MMA.  128 -> 64 at 256^2:
+            # 0.27 ms per 16 images vs 0.46 ms for the four row-slab phase launches (1.0 PFLOP/s, 0.71 of the sustained bf16 peak)
+            wn = f"{s}.0.weight"
+            wsl = self._slab_cached(P, (s, "convT_ring_w"), [wn], lambda: slab.convt_ring_weights(P[wn].detach()))
+            y0 = torch.empty((N, 2 * a_in.shape[1], 2 * a_in.shape[2], C), device=dev, dtype=dtype)
+            slab.convt_ring(a_in, wsl, self._bias(P, f"{s}.0"), C, out=y0, stats=st0)
+        elif (self.convT_slab and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
                 C % 16 == 0 and C * self.inwidth[s] <= 64 * 128 and a_in.shape[2] % 8 == 0):
             # (weights of a phase resident in shared memory: 128 -> 64 measured 0.64 -> 0.49 ms per 16 images at 256^2;
             #  with streamed weights, 256 -> 128, the per-tap TMA kernel is as fast: 0.36 vs 0.38 ms)

@@ -490,3 +490,78 @@ def msb_ring(x, w_stacks, bias, C=64, out=None, co_off=0, stats=None, ci_off=0):
 
 def msb64_ring(x, w_stacks, bias, out=None, co_off=0, stats=None, ci_off=0):
     return msb_ring(x, w_stacks, bias, 64, out, co_off, stats, ci_off)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ConvTranspose2d(k = 4, stride 2, pad 1) as a ROW RING (csrc/convt_ring.cu): out[o, u] = sum in[i, j] w[ky, kx] with
+# o = 2 i - 1 + ky, u = 2 j - 1 + kx.  One launch per horizontal output phase px = u mod 2 (and per 64 output channels); a CTA walks
+# down a 128-pixel column strip of the input.  Input row r feeds the output rows 2r-1 .. 2r+2 (ky = 0..3), whose accumulators are
+# adjacent 64-column slots of an eight-slot ring (slot = output row mod 8), so for each of the phase's two horizontal taps the four
+# vertical taps are ONE MMA of N = 256 over the stack [ky = 0 | 1 | 2 | 3].  Input row r completes the output rows 2r-1 and 2r.
+# The functions below ARE the schedule (the CUDA kernel restates them; tests/test_convt_ring_cpu.py runs them on tensors).
+# ---------------------------------------------------------------------------------------------------------------------
+CONVT_RING_KX = ((1, 3), (2, 0))        # [px] -> kx of the phase's two horizontal taps ...
+CONVT_RING_DX = ((0, -1), (0, 1))       # ... and the input pixel they read relative to the output pixel pair (u = 2 j' + px)
+CONVT_RING_SLOTS = 8
+CONVT_RING_LEAD = 3                     # steps (input rows) the issuer may run ahead of the epilogue: a slot is touched again 3 rows later
+
+
+def convt_ring_row_mmas(r, y0, y1):
+    """MMAs input row r issues for the piece of input rows [y0, y1) (output rows [2 y0, 2 y1)), per horizontal tap:
+    [(first entry e0 = ky, number of stacked entries, first TMEM column)]"""
+    runs, run = [], []
+    for e in range(4):
+        o = 2 * r - 1 + e
+        if not (2 * y0 <= o < 2 * y1):
+            if run:
+                runs.append(run)
+            run = []
+            continue
+        c = (o % CONVT_RING_SLOTS) * 64
+        if run and c == run[-1][1] + 64:
+            run.append((e, c))
+        else:
+            if run:
+                runs.append(run)
+            run = [(e, c)]
+    if run:
+        runs.append(run)
+    return [(rn[0][0], len(rn), rn[0][1]) for rn in runs]
+
+
+def convt_ring_weights(w, dtype=torch.bfloat16):
+    """w: ConvTranspose2d weight [Cin, Cout, 4, 4] -> [Cout/64][2 px][Cin/64][2 taps][4 ky][64 co][64 ci] as rows of 64"""
+    Cin, Cout = w.shape[0], w.shape[1]
+    out = []
+    for g in range(Cout // 64):
+        for px in range(2):
+            for kb in range(Cin // 64):
+                for t in range(2):
+                    kx = CONVT_RING_KX[px][t]
+                    for ky in range(4):
+                        out.append(w[kb * 64:(kb + 1) * 64, g * 64:(g + 1) * 64, ky, kx].t())
+    return torch.cat(out, 0).to(dtype).contiguous()
+
+
+def convt_ring_supported(x, Cin, Cout):
+    return x.dtype == torch.bfloat16 and Cin in (64, 128) and Cout % 64 == 0
+
+
+def convt_ring(x, w_stacks, bias, Cout, out=None, co_off=0, stats=None, ci_off=0, Cin=None):
+    """ConvTranspose2d(4, 2, 1): x [N,H,W,>=Cin] bf16 -> out [N,2H,2W,Co_total] bf16 (Cout channels at co_off), IN statistics
+    accumulated into stats.  w_stacks = convt_ring_weights(weight)."""
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    Cin = Ci_total if Cin is None else Cin
+    if out is None:
+        out = torch.empty((N, 2 * H, 2 * W, Cout), device=x.device, dtype=torch.bfloat16)
+    rows = (Cout // 64) * 2 * (Cin // 64) * 512
+    if tuple(w_stacks.shape) != (rows, 64) or w_stacks.dtype != torch.bfloat16:
+        raise ValueError(f"convt_ring: w_stacks must be bf16 [{rows}, 64] (convt_ring_weights), got {tuple(w_stacks.shape)}")
+    d = _lib.ConvtRingDesc()
+    d.dtype, d.N, d.H, d.W, d.Cin, d.Cout = _lib.BF16, N, H, W, Cin, Cout
+    d.Ci_total, d.ci_off, d.Co_total, d.co_off = Ci_total, ci_off, out.shape[3], co_off
+    d.flags = _lib.CONV_STATS if stats is not None else 0
+    _lib.call("msg_convt_ring", ctypes.byref(d), ops._p(x), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats), ops._stream())
+    _lib.launches += 2 * (Cout // 64) - 1           # one kernel per phase and 64 output channels
+    return out

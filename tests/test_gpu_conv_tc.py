@@ -343,3 +343,29 @@ def test_msb128_ring_matches_the_four_branch_convs(N, H, W):
     out2 = torch.zeros_like(out)
     slab.msb_ring(nhwc(x).bfloat16(), slab.msb_ring_weights(ws, C), bias, C, out=out2, co_off=C)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(1, 16, 128, 128, 64), (2, 40, 64, 128, 64), (1, 9, 20, 64, 64), (3, 33, 200, 128, 64),
+                                            (2, 64, 256, 128, 64), (1, 21, 136, 64, 128)])
+def test_convt_ring_matches_conv_transpose(N, H, W, Cin, Cout):
+    """csrc/convt_ring.cu (row ring of TMEM accumulators, the four vertical taps of a horizontal tap as one N = 256 MMA, one launch
+    per horizontal output phase) vs ConvTranspose2d(4, 2, 1) of the reference's decoder (enhanced_generator.py:116-123) on
+    bf16-rounded operands, with the IN statistics of its epilogue, written as a channel slice of a wider tensor."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(N * 1000 + H + W + Cin)
+    x = torch.randn(N, Cin, H, W, device=DEV).bfloat16().float()
+    w = (torch.randn(Cin, Cout, 4, 4, device=DEV) * (2.0 / (Cin * 4)) ** 0.5).bfloat16().float()
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    ref = F.conv_transpose2d(x, w, bias, stride=2, padding=1)
+    st = ops.new_stats(N, Cout + 64, DEV)
+    out = torch.zeros(N, 2 * H, 2 * W, Cout + 64, device=DEV, dtype=torch.bfloat16)
+    ws = slab.convt_ring_weights(w)
+    slab.convt_ring(nhwc(x).bfloat16(), ws, bias, Cout, out=out, co_off=64, stats=st)
+    torch.cuda.synchronize()
+    assert float(out[..., :64].abs().max()) == 0.0                          # only the slice is written
+    assert_parity(out[..., 64:].float().permute(0, 3, 1, 2), ref, 1e-2, f"convT ring {N}x{H}x{W} {Cin}->{Cout}")
+    assert_parity(st[:, 64:, 0].float(), ref.sum(dim=(2, 3)), 2e-3, "ring sum", floor=1e-2)
+    assert_parity(st[:, 64:, 1].float(), (ref * ref).sum(dim=(2, 3)), 2e-3, "ring sum of squares")
+    out2 = torch.zeros_like(out)
+    slab.convt_ring(nhwc(x).bfloat16(), ws, bias, Cout, out=out2, co_off=64)
+    assert torch.equal(out, out2)

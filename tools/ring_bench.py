@@ -35,8 +35,23 @@ def bench128(N, H, W):
     print(f"C=128 per-tap slab                       : {timed(lambda: slab.conv_slab(prog, x, wsl, bias, out=out, stats=st)):.4f} ms")
 
 
+def bench_convt(N, H, W, Cin=128, Cout=64):
+    x = torch.randn(N, H, W, Cin, device="cuda").bfloat16()
+    w = torch.randn(Cin, Cout, 4, 4, device="cuda") * 0.05
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    out = torch.empty(N, 2 * H, 2 * W, Cout, device="cuda", dtype=torch.bfloat16)
+    st = ops.new_stats(N, Cout, "cuda")
+    wr = slab.convt_ring_weights(w)
+    print(f"convT {Cin}->{Cout} {N}x{H}x{W} ring (2 phases), stats : {timed(lambda: slab.convt_ring(x, wr, bias, Cout, out=out, stats=st)):.4f} ms")
+    g = ops.ConvGeom("convT", Cin, Cout, 4, 2, 1)
+    progs = slab.convT_phase_programs(Cin, Cout)
+    wsl = slab.convT_phase_weight_slabs(progs, g.pack_fwd(w, torch.bfloat16), Cin, Cout)
+    print(f"convT row-slab phases (4 launches)              : {timed(lambda: slab.convT_slab(progs, x, wsl, bias, out, stats=st)):.4f} ms")
+
+
 def main():
     N, H, W = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (16, 512, 512)
+    bench_convt(N, H // 2, W // 2)
     bench128(N, H // 2, W // 2)
     torch.manual_seed(0)
     x = torch.randn(N, H, W, 64, device="cuda").bfloat16()
