@@ -282,6 +282,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
                            "algorithmic_gflop_per_image_forward": gflop * scale,
                            "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",
                            "launches_per_step": conv_launches, "ms_per_step": conv_ms,
+                           "launches_note": "C-ABI calls; msg_msb_ring at C = 128 is 3 kernels per call, msg_convt_ring 2",
                            "measured_on": f"serialised pass of the same step (one stream, no graph replay, {ms_serial:.1f} ms per step): "
                                           "launches inside a replayed graph cannot be bracketed by events"}
     in_keys = ("msg_instnorm_apply", "msg_instnorm_stats")

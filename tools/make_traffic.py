@@ -5,7 +5,7 @@
     python tools/make_traffic.py gpurun_out/stylise_launches.csv profiles/r2_stylise_launch_list.md
 
 The LAST forward (from the last nchw_to_nhwc launch to the last blend) is taken as the sample; the tensor-core family is every
-conv_tma / conv_slab / conv_shift / conv_tc / msb64_ring / la_stage / local_attn_fwd_tc launch in it (bench.py's roofline family)."""
+conv_tma / conv_slab / conv_shift / conv_tc / msb_ring / convt_ring / la_stage / local_attn_fwd_tc launch in it (bench.py's roofline family)."""
 import collections
 import csv
 import json
@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-FAMILY = re.compile(r"conv_tma_kernel|conv_slab_kernel|conv_shift_kernel|conv_tc_kernel|msb64_ring_kernel|la_stage_kernel|local_attn_fwd_tc_kernel")
+FAMILY = re.compile(r"conv_tma_kernel|conv_slab_kernel|conv_shift_kernel|conv_tc_kernel|msb64_ring_kernel|msb_ring_kernel|convt_ring_kernel|la_stage_kernel|local_attn_fwd_tc_kernel")
 
 
 def main():
