@@ -255,7 +255,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
     H = W = args.size
     scale = (H * W) / 512 ** 2
     out = {}
-    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_msb64_ring", "msg_msb_ring", "msg_convt_ring", "msg_la_stage_fwd",
+    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_msb64_ring", "msg_msb_ring", "msg_convt_ring", "msg_out7_ring", "msg_la_stage_fwd",
                  "msg_local_attn_fwd")
     conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in conv_keys) / args.steps
     conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in conv_keys) // args.steps
@@ -274,6 +274,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
                                      + (" + msb_ring_kernel" if (breakdown.get("msg_msb64_ring", {}).get("launches", 0)
                                                                  or breakdown.get("msg_msb_ring", {}).get("launches", 0)) else "")
                                      + (" + convt_ring_kernel" if breakdown.get("msg_convt_ring", {}).get("launches", 0) else "")
+                                     + (" + out7_ring_kernel" if breakdown.get("msg_out7_ring", {}).get("launches", 0) else "")
                                      + (" + la_stage_kernel" if fused_la else "")
                                      + (" + local_attn_fwd_tc_kernel" if breakdown.get("msg_local_attn_fwd", {}).get("launches", 0) else "")
                                      + " (every tensor-core launch of the step)",

@@ -304,6 +304,21 @@ typedef struct {
 int msg_convt_ring(const msg_convt_ring_desc* d, const void* x, const void* w_stacks, const float* bias, void* y,
                    double* stats, void* stream);
 
+/* Output layer of the generator fused with the InstanceNorm + ReLU + residual in front of it (enhanced_generator.py:78-84, 130-133):
+ *   y = tanh(conv7x7(residual + ReLU(IN(f))) + bias), 64 -> 3 channels, fp32 NCHW out
+ * as a row ring of tensor-memory accumulators (csrc/out7_ring.cu): f and residual row slabs loaded once, normalised in shared memory
+ * (the apply kernel's arithmetic), the 7 vertical taps of a horizontal tap as ONE N = 112 MMA.  Inference only (a2 is not kept).
+ * f [N,H,W,Cf_total] bf16 raw conv output (channels [cf_off, +64)), in_stats fp64 [N][Cs_total][2] its raw plane sums (channels
+ * [cs_off, +64)), residual [N,H,W,Cr_total] bf16, w_stacks bf16 [896][64] (slab.out7_ring_weights), bias fp32 [3] or NULL,
+ * y fp32 [N,3,H,W]. */
+typedef struct {
+  int dtype;                 /* MSG_BF16 */
+  int N, H, W;
+  int Cf_total, cf_off, Cr_total, cr_off, Cs_total, cs_off;
+} msg_out7_ring_desc;
+int msg_out7_ring(const msg_out7_ring_desc* d, const void* f, const double* in_stats, const void* residual,
+                  const void* w_stacks, const float* bias, float* y, void* stream);
+
 /* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
  * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):
  * out fp32 NCHW [N,3,H,W] = (v / 255 - 0.5) / 0.5.  canvas (optional, may be NULL): the pasted uint8 canvas [N,H,W,3].

@@ -66,6 +66,11 @@ class ConvtRingDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Cin", "Cout", "Ci_total", "ci_off", "Co_total", "co_off")] + [("flags", c_uint)]
 
 
+class Out7RingDesc(ctypes.Structure):
+    """mirrors msg_out7_ring_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Cf_total", "cf_off", "Cr_total", "cr_off", "Cs_total", "cs_off")]
+
+
 SN_MAX_BATCH = 8
 
 
@@ -106,6 +111,7 @@ SIGNATURES = {
     "msg_msb64_ring": [ctypes.POINTER(MsbRingDesc), _P, _P, _P, _P, _P, _P],
     "msg_msb_ring": [ctypes.POINTER(MsbRingDesc), ctypes.c_int, _P, _P, _P, _P, _P, _P],
     "msg_convt_ring": [ctypes.POINTER(ConvtRingDesc), _P, _P, _P, _P, _P, _P],
+    "msg_out7_ring": [ctypes.POINTER(Out7RingDesc), _P, _P, _P, _P, _P, _P, _P],
     "msg_u8_canvas_to_nchw": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_u8_strength_blend": [_P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],

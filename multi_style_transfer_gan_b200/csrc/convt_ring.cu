@@ -179,22 +179,11 @@ convt_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tc_fence_after();
           if (leader) {
             const uint32_t a0 = (sA + s * STAGE) >> 4;
-            // entries e = ky = 0..3 = output rows 2r-1 .. 2r+2 (those of this piece); runs of adjacent ring slots merge
-            uint32_t col[4];
-            bool ok[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int o = 2 * r - 1 + e;
-              ok[e] = o >= 2 * y0 && o < 2 * y1;
-              col[e] = (uint32_t)((o & 7) * NC);
-            }
-            int e = 0;
-            while (e < 4) {
-              if (!ok[e]) { ++e; continue; }
-              int nrun = 1;
-              while (e + nrun < 4 && ok[e + nrun] && col[e + nrun] == col[e + nrun - 1] + (uint32_t)NC) ++nrun;
+            // entries e = ky = 0..3 = output rows 2r-1 .. 2r+2; those of this piece are an interval whose ring slots are adjacent
+            // except where the ring wraps: one or two runs, found by arithmetic (no run table in local memory)
+            auto issue_run = [&](int e, int nrun, int slot) {
               const uint32_t idesc = idesc0 | ((uint32_t)((NC * nrun) >> 3) << 17);
-              const uint32_t dcol = tmem_base + col[e];
+              const uint32_t dcol = tmem_base + (uint32_t)(slot * NC);
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 const uint32_t wrow = (uint32_t)(t * 4 * NC + NC * e);
@@ -206,7 +195,13 @@ convt_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     umma_bf16_lo(dcol, av + (uint32_t)(kb * (SLAB_BYTES >> 4) + 2 * ks),
                                  b_base + (uint32_t)(kb * W_ROWS * 8) + wrow * 8u + (uint32_t)(2 * ks), hi, idesc, true);
               }
-              e += nrun;
+            };
+            const int o_lo = 2 * r - 1 > 2 * y0 ? 2 * r - 1 : 2 * y0, o_hi = 2 * r + 2 < 2 * y1 - 1 ? 2 * r + 2 : 2 * y1 - 1;      // inclusive
+            if (o_lo <= o_hi) {
+              const int cnt = o_hi - o_lo + 1, slot = o_lo & 7;
+              const int n1 = cnt < 8 - slot ? cnt : 8 - slot;
+              issue_run(o_lo - (2 * r - 1), n1, slot);
+              if (cnt > n1) issue_run(o_lo - (2 * r - 1) + n1, cnt - n1, 0);
             }
             umma_commit(empty_bar(s));
           }

@@ -243,23 +243,14 @@ msb_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
               } else {
                 constexpr int d = ring_dil(b);
-                // entries e = 0, 1, 2 = output rows r - d, r, r + d (vertical taps ky = 2, 1, 0); runs of adjacent ring slots merge
-                uint32_t col[3];
-                bool ok[3];
+                // entries e = 0, 1, 2 = output rows r - d, r, r + d (vertical taps ky = 2, 1, 0); those of this piece are an interval
+                // of entries whose slots in the residue class's ring are adjacent except where the ring wraps: one or two runs,
+                // found by arithmetic (no run table in local memory)
+                constexpr int R = ring_slots(C, PS, I);
                 const uint32_t set = ring_dup(C, PS, I) > 1 ? (uint32_t)((r & 1) * ring_width(C, PS, I)) : 0u;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                  const int y = r + (e - 1) * d;
-                  ok[e] = y >= y0 && y < y1;
-                  col[e] = ok[e] ? ring_col<C, PS, I>(y) + set : 0u;
-                }
-                int e = 0;
-                while (e < 3) {
-                  if (!ok[e]) { ++e; continue; }
-                  int nrun = 1;
-                  while (e + nrun < 3 && ok[e + nrun] && col[e + nrun] == col[e + nrun - 1] + (uint32_t)Q) ++nrun;
+                auto issue_run = [&](int e, int nrun, int idx, int cls) {
                   const uint32_t idesc = idesc0 | ((uint32_t)((Q * nrun) >> 3) << 17);
-                  const uint32_t dcol = tmem_base + col[e];
+                  const uint32_t dcol = tmem_base + (uint32_t)(ring_base(C, PS, I) + (cls * R + idx) * Q) + set;
 #pragma unroll
                   for (int kx = 0; kx < 3; ++kx) {
                     const uint32_t wrow = wr0 + (uint32_t)(kx * 3 * Q + Q * e);
@@ -271,7 +262,15 @@ msb_ring_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         umma_bf16_lo(dcol, av + (uint32_t)(kb * (SLAB_BYTES >> 4) + 2 * ks),
                                      b_base + (uint32_t)(kb * ROWS * 8) + wrow * 8u + (uint32_t)(2 * ks), hi, idesc, true);
                   }
-                  e += nrun;
+                };
+                const int e_lo = r - d >= y0 ? 0 : (r >= y0 ? 1 : 2);                // r + d >= y0 holds for every row of the piece's halo
+                const int e_hi = r + d < y1 ? 2 : (r < y1 ? 1 : 0);                  // r - d < y1 likewise
+                if (e_lo <= e_hi && r + d >= y0 && r - d < y1) {
+                  const int ylo = r + (e_lo - 1) * d;                                // first output row (>= y0 >= 0)
+                  const int cnt = e_hi - e_lo + 1, idx = (ylo / d) % R, cls = ylo % d;
+                  const int n1 = cnt < R - idx ? cnt : R - idx;
+                  issue_run(e_lo, n1, idx, cls);
+                  if (cnt > n1) issue_run(e_lo + n1, cnt - n1, 0, cls);
                 }
               }
             };

@@ -109,6 +109,8 @@ class GeneratorEngine:
         self.msb128_ring = os.environ.get("MSG_MSB128_RING", "1") == "1"
         # ... and for the 128 -> 64 transposed conv of up2 (csrc/convt_ring.cu).  MSG_CONVT_RING=0 falls back to the phase slabs.
         self.convT_ring = os.environ.get("MSG_CONVT_RING", "1") == "1"
+        # ... and for the output conv fused with the IN + ReLU + residual in front of it (csrc/out7_ring.cu).  MSG_OUT7_RING=0 falls back.
+        self.out7_ring = os.environ.get("MSG_OUT7_RING", "1") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
@@ -166,7 +168,7 @@ class GeneratorEngine:
         return b.contiguous()
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _stage_fwd(self, P, s, a_in, dtype, keep=True, arena=None):
+    def _stage_fwd(self, P, s, a_in, dtype, keep=True, arena=None, defer_apply=False):
         """keep=False (inference): intermediates are dropped as soon as their consumer has been
         launched, so the caching allocator recycles them within the stage."""
         g = self.geom
@@ -204,7 +206,7 @@ class GeneratorEngine:
             # exist in HBM (csrc/la_stage.cu)
             a1 = ops.la_stage_fwd(y0, wq, self._bias(P, f"{s}.3.qkv"), wp, self._bias(P, f"{s}.3.proj"), in_stats=st0, in_act=ACT_RELU)
             del y0
-            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C)
+            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C, defer_apply)
         if not keep and self.fuse_in_norm and g[f"{s}.3.qkv"].fused_in_norm_ok(y0, wq):
             # inference: ReLU(IN(y0)) has ONE consumer, the 1x1 qkv conv (LocalAttention has no residual), so the
             # conv normalises its A tiles in shared memory and the normalised tensor never exists in HBM
@@ -219,10 +221,10 @@ class GeneratorEngine:
         a1 = g[f"{s}.3.proj"].forward(att, wp, self._bias(P, f"{s}.3.proj"))
         if not keep:
             del att
-            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C)
+            return self._msb_fwd(P, s, a1, None, dtype, keep, arena, g, C, defer_apply)
         return self._msb_fwd(P, s, a1, dict(a_in=a_in, y0=y0, st0=st0, a0=a0, qkv=qkv, att=att), dtype, keep, arena, g, C)
 
-    def _msb_fwd(self, P, s, a1, saved, dtype, keep, arena, g, C):
+    def _msb_fwd(self, P, s, a1, saved, dtype, keep, arena, g, C, defer_apply=False):
         """MultiScaleBlock of stage s on a1 (enhanced_generator.py:78-84)."""
         dev = a1.device
         b = torch.empty_like(a1)
@@ -258,6 +260,9 @@ class GeneratorEngine:
         else:
             bn = ops.instnorm_apply(b, stb, ACT_RELU, out=None if keep else b)
             f = g[n].forward(bn, wf, self._bias(P, n), stats=stf)
+        if defer_apply and not keep:
+            # the stage's last IN + ReLU + residual is applied by its consumer on the landed row slabs (csrc/out7_ring.cu)
+            return (f, stf, a1), None
         a2 = ops.instnorm_apply(f, stf, ACT_RELU, residual=a1, out=None if keep else f)
         if not keep:
             return a2, None
@@ -296,11 +301,21 @@ class GeneratorEngine:
         """a: [N,H/4,W/4,4c] NHWC -> (y fp32 NCHW in [-1,1], saved)."""
         saved = {} if save else None
         arena = _StatsArena(a.shape[0], 3 * (self.width["up1"] + self.width["up2"]), a.device)
+        # inference at c = 64 (bf16): the output conv applies up2's last IN + ReLU + residual itself (one ring kernel instead of the
+        # HBM-bound apply + the taps-as-N conv: csrc/out7_ring.cu)
+        fuse_out = (not save and self.out7_ring and dtype == torch.bfloat16 and self.c == 64 and self.use_slab)
         for s in ("up1", "up2"):
             a_in = a
-            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"), arena=arena)
+            a, sv = self._stage_fwd(P, s, a_in, dtype, keep=(save == "full"), arena=arena, defer_apply=(fuse_out and s == "up2"))
             if save:
                 saved[s] = sv if save == "full" else {"a_in": a_in}
+        if isinstance(a, tuple):
+            f, stf, a1 = a
+            N, H, W, _ = f.shape
+            y = torch.empty((N, 3, H, W), device=f.device, dtype=torch.float32)
+            wsl = self._slab_cached(P, ("output", "ring_w"), ["output.0.weight"], lambda: slab.out7_ring_weights(P["output.0.weight"].detach()))
+            slab.out7_ring(f, stf, a1, wsl, P["output.0.bias"].detach().contiguous(), nchw_out=y)
+            return y, saved
         N, H, W, _ = a.shape
         y = torch.empty((N, 3, H, W), device=a.device, dtype=torch.float32)
         if self.use_slab and dtype == torch.bfloat16 and self._out_prog is not None and W % 8 == 0:

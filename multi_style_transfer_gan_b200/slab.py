@@ -565,3 +565,65 @@ def convt_ring(x, w_stacks, bias, Cout, out=None, co_off=0, stats=None, ci_off=0
     _lib.call("msg_convt_ring", ctypes.byref(d), ops._p(x), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats), ops._stream())
     _lib.launches += 2 * (Cout // 64) - 1           # one kernel per phase and 64 output channels
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Output layer Conv2d(64, 3, 7, padding 3) + Tanh fused with the IN + ReLU + residual in front of it, as a ROW RING
+# (csrc/out7_ring.cu).  Input row r feeds the output rows r-3 .. r+3 (ky = 6 .. 0): 16-column slots (3 channels padded) of a
+# 32-slot ring, so for each horizontal tap (a shifted view of the slab) the 7 vertical taps are ONE MMA of N = 112 over the stack
+# [ky = 6 | 5 | ... | 0]; input row r completes output row r-3.
+# ---------------------------------------------------------------------------------------------------------------------
+OUT7_RING_SLOTS = 32
+OUT7_RING_LEAD = 6
+
+
+def out7_ring_row_mmas(r, y0, y1):
+    """MMAs input row r issues per horizontal tap for the piece of rows [y0, y1): [(first entry e0, entries, first TMEM column)];
+    entry e = output row r - 3 + e = vertical tap ky = 6 - e"""
+    runs, run = [], []
+    for e in range(7):
+        o = r - 3 + e
+        if not (y0 <= o < y1):
+            if run:
+                runs.append(run)
+            run = []
+            continue
+        c = (o % OUT7_RING_SLOTS) * 16
+        if run and c == run[-1][1] + 16:
+            run.append((e, c))
+        else:
+            if run:
+                runs.append(run)
+            run = [(e, c)]
+    if run:
+        runs.append(run)
+    return [(rn[0][0], len(rn), rn[0][1]) for rn in runs]
+
+
+def out7_ring_weights(w, dtype=torch.bfloat16):
+    """w: Conv2d weight [3, 64, 7, 7] -> [7 kx][8 entries][16 co][64 ci] as rows of 64 (entry e < 7 = ky 6 - e, channels 3..15 and
+    entry 7 zero)"""
+    out = torch.zeros(7, 8, 16, 64, device=w.device, dtype=w.dtype)
+    for kx in range(7):
+        for e in range(7):
+            out[kx, e, :3] = w[:, :, 6 - e, kx]
+    return out.reshape(7 * 128, 64).to(dtype).contiguous()
+
+
+def out7_ring(f, in_stats, residual, w_stacks, bias, nchw_out=None):
+    """y = tanh(conv7x7(residual + ReLU(IN(f))) + bias): f, residual [N,H,W,64] bf16, in_stats fp64 [N,64,2] (raw plane sums of f)
+    -> fp32 [N,3,H,W]."""
+    ops._dev(f)
+    N, H, W, Cf = f.shape
+    if f.dtype != torch.bfloat16 or residual.dtype != torch.bfloat16 or residual.shape[:3] != f.shape[:3]:
+        raise ValueError("out7_ring: f and residual must be bf16 NHWC tensors of the same plane")
+    if tuple(w_stacks.shape) != (896, 64) or w_stacks.dtype != torch.bfloat16:
+        raise ValueError(f"out7_ring: w_stacks must be bf16 [896, 64] (out7_ring_weights), got {tuple(w_stacks.shape)}")
+    if nchw_out is None:
+        nchw_out = torch.empty((N, 3, H, W), device=f.device, dtype=torch.float32)
+    d = _lib.Out7RingDesc()
+    d.dtype, d.N, d.H, d.W = _lib.BF16, N, H, W
+    d.Cf_total, d.cf_off, d.Cr_total, d.cr_off, d.Cs_total, d.cs_off = Cf, 0, residual.shape[3], 0, in_stats.shape[1], 0
+    _lib.call("msg_out7_ring", ctypes.byref(d), ops._p(f), ops._p(in_stats), ops._p(residual), ops._p(w_stacks), ops._p(bias),
+              ops._p(nchw_out), ops._stream())
+    return nchw_out

@@ -369,3 +369,30 @@ def test_convt_ring_matches_conv_transpose(N, H, W, Cin, Cout):
     out2 = torch.zeros_like(out)
     slab.convt_ring(nhwc(x).bfloat16(), ws, bias, Cout, out=out2, co_off=64)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 16, 128), (2, 40, 64), (1, 9, 20), (3, 33, 200), (2, 64, 256), (1, 130, 136)])
+def test_out7_ring_matches_apply_plus_output_conv(N, H, W):
+    """csrc/out7_ring.cu: y = tanh(conv7x7(a1 + ReLU(IN(f))) + b) in one launch (IN + ReLU + residual applied to the landed row slabs,
+    7 vertical taps as one N = 112 MMA through a ring of TMEM row accumulators) vs the reference's modules
+    (enhanced_generator.py:78-84, 130-133) on the same bf16-rounded a2, and vs the product's two-kernel path (apply kernel +
+    conv_shift), whose a2 it must reproduce bit for bit."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(N * 1000 + H + W + 3)
+    f = (torch.randn(N, 64, H, W, device=DEV) * 1.7 + 0.3).bfloat16()
+    a1 = torch.randn(N, 64, H, W, device=DEV).bfloat16()
+    w = (torch.randn(3, 64, 7, 7, device=DEV) * (1.0 / (64 * 49)) ** 0.5).bfloat16().float()
+    bias = torch.randn(3, device=DEV) * 0.1
+    fh, ah = nhwc(f), nhwc(a1)
+    st = ops.instnorm_stats(fh)
+    a2 = ops.instnorm_apply(fh, st, ops.ACT_RELU, residual=ah)              # the product's apply kernel (bf16 out)
+    ref = torch.tanh(F.conv2d(a2.float().permute(0, 3, 1, 2), w, bias, padding=3))
+    got = slab.out7_ring(fh, st, ah, slab.out7_ring_weights(w), bias)
+    torch.cuda.synchronize()
+    assert_parity(got, ref, 2e-3, f"out7 ring {N}x{H}x{W}")
+    # and against fp32 modules end to end (bf16 operand rounding only)
+    x32 = a1.float() + torch.relu(F.instance_norm(f.float()))
+    ref32 = torch.tanh(F.conv2d(x32, w, bias, padding=3))
+    assert_parity(got, ref32, 1e-2, "out7 ring vs fp32 modules")
+    got2 = slab.out7_ring(fh, st, ah, slab.out7_ring_weights(w), bias)
+    assert torch.equal(got, got2)

@@ -49,8 +49,28 @@ def bench_convt(N, H, W, Cin=128, Cout=64):
     print(f"convT row-slab phases (4 launches)              : {timed(lambda: slab.convT_slab(progs, x, wsl, bias, out, stats=st)):.4f} ms")
 
 
+def bench_out7(N, H, W):
+    f = torch.randn(N, H, W, 64, device="cuda").bfloat16()
+    a1 = torch.randn(N, H, W, 64, device="cuda").bfloat16()
+    w = torch.randn(3, 64, 7, 7, device="cuda") * 0.02
+    bias = torch.randn(3, device="cuda") * 0.1
+    st = ops.instnorm_stats(f)
+    y = torch.empty(N, 3, H, W, device="cuda")
+    wr = slab.out7_ring_weights(w)
+    print(f"output layer {N}x{H}x{W}: fused ring (apply + conv7 + tanh) : {timed(lambda: slab.out7_ring(f, st, a1, wr, bias, nchw_out=y)):.4f} ms")
+    prog = slab.conv7_out_shift_program(64)
+    wsl = slab.conv7_out_shift_weights(prog, w)
+    a2 = torch.empty_like(f)
+
+    def two():
+        ops.instnorm_apply(f, st, ops.ACT_RELU, residual=a1, out=a2)
+        slab.conv_shift(prog, a2, wsl, bias, act=ops.ACT_TANH, nchw_out=y)
+    print(f"apply kernel + taps-as-N conv (2 launches)                : {timed(two):.4f} ms")
+
+
 def main():
     N, H, W = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (16, 512, 512)
+    bench_out7(N, H, W)
     bench_convt(N, H // 2, W // 2)
     bench128(N, H // 2, W // 2)
     torch.manual_seed(0)
