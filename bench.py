@@ -255,7 +255,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
     H = W = args.size
     scale = (H * W) / 512 ** 2
     out = {}
-    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_msb64_ring", "msg_msb_ring", "msg_convt_ring", "msg_out7_ring", "msg_la_stage_fwd",
+    conv_keys = ("msg_conv2d", "msg_conv_slab", "msg_conv_shift", "msg_msb64_ring", "msg_msb_ring", "msg_convt_ring", "msg_out7_ring", "msg_down_ring", "msg_la_stage_fwd",
                  "msg_local_attn_fwd")
     conv_ms = sum(breakdown.get(k, {}).get("ms", 0.0) for k in conv_keys) / args.steps
     conv_launches = sum(breakdown.get(k, {}).get("launches", 0) for k in conv_keys) // args.steps
@@ -275,6 +275,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
                                                                  or breakdown.get("msg_msb_ring", {}).get("launches", 0)) else "")
                                      + (" + convt_ring_kernel" if breakdown.get("msg_convt_ring", {}).get("launches", 0) else "")
                                      + (" + out7_ring_kernel" if breakdown.get("msg_out7_ring", {}).get("launches", 0) else "")
+                                     + (" + down_ring_kernel" if breakdown.get("msg_down_ring", {}).get("launches", 0) else "")
                                      + (" + la_stage_kernel" if fused_la else "")
                                      + (" + local_attn_fwd_tc_kernel" if breakdown.get("msg_local_attn_fwd", {}).get("launches", 0) else "")
                                      + " (every tensor-core launch of the step)",
@@ -283,7 +284,7 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
                            "algorithmic_gflop_per_image_forward": gflop * scale,
                            "peak_source": pk["source"] + " (sustained bf16; kernel timed inside a long step)",
                            "launches_per_step": conv_launches, "ms_per_step": conv_ms,
-                           "launches_note": "C-ABI calls; msg_msb_ring at C = 128 is 3 kernels per call, msg_convt_ring 2",
+                           "launches_note": "C-ABI calls; msg_msb_ring at C = 128 is 3 kernels per call, msg_convt_ring and msg_down_ring 2",
                            "measured_on": f"serialised pass of the same step (one stream, no graph replay, {ms_serial:.1f} ms per step): "
                                           "launches inside a replayed graph cannot be bracketed by events"}
     in_keys = ("msg_instnorm_apply", "msg_instnorm_stats")

@@ -319,6 +319,22 @@ typedef struct {
 int msg_out7_ring(const msg_out7_ring_desc* d, const void* f, const double* in_stats, const void* residual,
                   const void* w_stacks, const float* bias, float* y, void* stream);
 
+/* First down-sampling conv of the encoder, Conv2d(64, Cout, 4, stride 2, padding 1) (enhanced_generator.py:99-104), optionally fused
+ * with the InstanceNorm + ReLU in front of it (in_stats != NULL: x is the RAW output of the previous conv and in_stats its plane sums),
+ * as a row ring of tensor-memory accumulators (csrc/down_ring.cu): one launch per 64 output channels, every input row loaded once per
+ * launch as its even and its odd pixels, the two vertical taps of a horizontal tap as ONE N = 128 MMA.
+ * x [N,H,W,Ci_total] bf16 (channels [ci_off, +64)), H and W even; w_stacks bf16 (slab.down_ring_weights); bias fp32 [Cout] or NULL;
+ * y [N,H/2,W/2,Co_total] bf16 (channels [co_off, +Cout)); stats fp64 [N][Co_total][2] with MSG_CONV_STATS. */
+typedef struct {
+  int dtype;                 /* MSG_BF16 */
+  int N, H, W;               /* input plane */
+  int Cout;
+  int Ci_total, ci_off, Co_total, co_off, Cs_total, cs_off;
+  unsigned flags;            /* MSG_CONV_STATS */
+} msg_down_ring_desc;
+int msg_down_ring(const msg_down_ring_desc* d, const void* x, const double* in_stats, const void* w_stacks, const float* bias,
+                  void* y, double* stats, void* stream);
+
 /* uint8 pre-processing on the device (batch_process_images.py:193-205, 287-291): paste the [N,h,w,3] uint8 images (PIL layout) at
  * (off_y, off_x) on an HxW canvas filled with `fill` (the reference's white canvas), then ToTensor + Normalize(0.5, 0.5):
  * out fp32 NCHW [N,3,H,W] = (v / 255 - 0.5) / 0.5.  canvas (optional, may be NULL): the pasted uint8 canvas [N,H,W,3].

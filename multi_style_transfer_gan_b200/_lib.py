@@ -71,6 +71,11 @@ class Out7RingDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Cf_total", "cf_off", "Cr_total", "cr_off", "Cs_total", "cs_off")]
 
 
+class DownRingDesc(ctypes.Structure):
+    """mirrors msg_down_ring_desc (include/msg_b200.h)"""
+    _fields_ = [(n, c_int) for n in ("dtype", "N", "H", "W", "Cout", "Ci_total", "ci_off", "Co_total", "co_off", "Cs_total", "cs_off")] + [("flags", c_uint)]
+
+
 SN_MAX_BATCH = 8
 
 
@@ -112,6 +117,7 @@ SIGNATURES = {
     "msg_msb_ring": [ctypes.POINTER(MsbRingDesc), ctypes.c_int, _P, _P, _P, _P, _P, _P],
     "msg_convt_ring": [ctypes.POINTER(ConvtRingDesc), _P, _P, _P, _P, _P, _P],
     "msg_out7_ring": [ctypes.POINTER(Out7RingDesc), _P, _P, _P, _P, _P, _P, _P],
+    "msg_down_ring": [ctypes.POINTER(DownRingDesc), _P, _P, _P, _P, _P, _P, _P],
     "msg_u8_canvas_to_nchw": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "msg_u8_strength_blend": [_P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P],
     "msg_adam_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, _P],

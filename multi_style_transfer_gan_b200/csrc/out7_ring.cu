@@ -282,23 +282,37 @@ out7_ring_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant
       for (int r = r_lo; r < r_hi; ++r, ++n) {
         mbar_wait(full_bar(s), (n / S) & 1);
         uint8_t* fs = gen + (sA - base) + s * STAGE + rbase * 128 + pchunk * 16;
+        // (loads batched ahead of the arithmetic, no branches: rows 128..135 exist only for rbase < 8 -- those threads' ninth chunk --
+        // and out-of-plane pixels are forced to 0 by a select: the conv's zero padding is a padding of a2)
+        {
+          uint4 raw[9], res[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int px = rbase + 16 * i;
-          if (px < SLAB_PX) {
-            uint4* ptr = reinterpret_cast<uint4*>(fs + i * (16 * 128));
-            const int x = x0 + px;
-            if (x < 0 || x >= p.W) {
-              *ptr = make_uint4(0u, 0u, 0u, 0u);       // the conv's zero padding is a padding of a2
-            } else {
-              float fv[8], av[8];
-              unpack8(*ptr, fv);
-              unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(ptr) + SLAB_BYTES), av);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) fv[e] = fmaxf(fmaf(fv[e], sc[e], sh[e]), 0.f) + av[e];
-              *ptr = pack8(fv);
+          for (int i = 0; i < 9; ++i)
+            if (i < 8 || rbase < 8) {
+              raw[i] = *reinterpret_cast<const uint4*>(fs + i * (16 * 128));
+              res[i] = *reinterpret_cast<const uint4*>(fs + SLAB_BYTES + i * (16 * 128));
             }
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int x = x0 + rbase + 16 * i;
+            const bool inside = x >= 0 && x < p.W;
+            uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+            const uint32_t r4[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // packed f32x2 arithmetic with the apply kernel's roundings: fmaf, max 0, + residual, one bf16 RN pack
+              const float2 x2 = make_float2(__uint_as_float(w4[j] << 16), __uint_as_float(w4[j] & 0xffff0000u));
+              const float2 a2 = make_float2(__uint_as_float(r4[j] << 16), __uint_as_float(r4[j] & 0xffff0000u));
+              float2 o2 = __ffma2_rn(x2, make_float2(sc[2 * j], sc[2 * j + 1]), make_float2(sh[2 * j], sh[2 * j + 1]));
+              o2 = __fadd2_rn(make_float2(fmaxf(o2.x, 0.f), fmaxf(o2.y, 0.f)), a2);
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(o2.x, o2.y);
+              w4[j] = inside ? *reinterpret_cast<const uint32_t*>(&pk) : 0u;
+            }
+            raw[i] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+            if (i < 8 || rbase < 8) *reinterpret_cast<uint4*>(fs + i * (16 * 128)) = raw[i];
         }
         fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
         __syncwarp();

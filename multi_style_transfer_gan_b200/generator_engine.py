@@ -111,6 +111,8 @@ class GeneratorEngine:
         self.convT_ring = os.environ.get("MSG_CONVT_RING", "1") == "1"
         # ... and for the output conv fused with the IN + ReLU + residual in front of it (csrc/out7_ring.cu).  MSG_OUT7_RING=0 falls back.
         self.out7_ring = os.environ.get("MSG_OUT7_RING", "1") == "1"
+        # ... and for down1's 4x4 stride-2 conv fused with the input layer's IN + ReLU (csrc/down_ring.cu).  MSG_DOWN_RING=0 falls back.
+        self.down_ring = os.environ.get("MSG_DOWN_RING", "1") == "1"
         self.fuse_in_norm = os.environ.get("MSG_FUSE_IN_NORM", "1") == "1"
         self.fuse_la = os.environ.get("MSG_FUSE_LA", "1") == "1"      # fused LocalAttention stage kernel (inference)
         self._arena_floats = 0          # packed-gradient floats of one backward (measured on the first one)
@@ -173,12 +175,20 @@ class GeneratorEngine:
         launched, so the caching allocator recycles them within the stage."""
         g = self.geom
         C = self.width[s]
-        N = a_in.shape[0]
-        dev = a_in.device
+        x_in = a_in[0] if isinstance(a_in, tuple) else a_in       # (a tuple: raw conv output + its statistics, normalised by the consumer)
+        N = x_in.shape[0]
+        dev = x_in.device
         if arena is None:
             arena = _StatsArena(N, 3 * C, dev)
         st0 = arena.take(C)
-        if (self.convT_ring and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] in (64, 128) and C % 64 == 0):
+        if isinstance(a_in, tuple):
+            # inference, c = 64: the IN + ReLU of the 7x7 input layer is applied by this stage's 4x4 stride-2 conv on its landed row
+            # slabs (csrc/down_ring.cu: 0.50 -> ~0.3 ms per 16 images for apply + conv, the normalised tensor never exists in HBM)
+            yi, sti = a_in
+            wn = f"{s}.0.weight"
+            wsl = self._slab_cached(P, (s, "down_ring_w"), [wn], lambda: slab.down_ring_weights(P[wn].detach()))
+            y0 = slab.down_ring(yi, sti, wsl, self._bias(P, f"{s}.0"), C, stats=st0)
+        elif (self.convT_ring and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] in (64, 128) and C % 64 == 0):
             # transposed conv as a row ring of TMEM accumulators (csrc/convt_ring.cu): one launch per horizontal output phase, every
             # input row loaded once per launch, the four vertical taps of a horizontal tap as one N = 256 MMA.  128 -> 64 at 256^2:
             # 0.27 ms per 16 images vs 0.46 ms for the four row-slab phase launches (1.0 PFLOP/s, 0.71 of the sustained bf16 peak)
@@ -288,7 +298,10 @@ class GeneratorEngine:
             yi = slab.conv_slab(prog, x0, wsl, self._bias(P, "initial.0"), stats=sti)
         else:
             yi = self._g("initial.0", dtype).forward(x0, self._packed(P, "initial.0", "fwd", dtype), self._bias(P, "initial.0"), stats=sti)
-        a = ops.instnorm_apply(yi, sti, ACT_RELU, out=None if save else yi)
+        if not save and self.down_ring and dtype == torch.bfloat16 and self.c == 64 and self.use_slab and H % 2 == 0 and W % 2 == 0:
+            a = (yi, sti)           # applied by down1's first conv (csrc/down_ring.cu)
+        else:
+            a = ops.instnorm_apply(yi, sti, ACT_RELU, out=None if save else yi)
         saved = {"x0": x0, "yi": yi, "sti": sti} if save else None
         for s in ("down1", "down2"):
             a_in = a

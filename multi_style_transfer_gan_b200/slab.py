@@ -627,3 +627,69 @@ def out7_ring(f, in_stats, residual, w_stacks, bias, nchw_out=None):
     _lib.call("msg_out7_ring", ctypes.byref(d), ops._p(f), ops._p(in_stats), ops._p(residual), ops._p(w_stacks), ops._p(bias),
               ops._p(nchw_out), ops._stream())
     return nchw_out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Conv2d(64, Cout, 4, stride 2, padding 1) (+ the IN + ReLU in front of it) as a ROW RING (csrc/down_ring.cu):
+# y[o, u] = sum a[2o - 1 + ky, 2u - 1 + kx] w[ky, kx].  A CTA walks down a strip of 128 output pixels; input row r arrives as its
+# even-pixel and its odd-pixel slab (kx = 0, 2 read the odd slab at u - 1, u; kx = 1, 3 the even slab at u, u + 1) and feeds the two
+# output rows (r - 1) // 2 and (r - 1) // 2 + 1 with the vertical taps ky = 3 - r % 2 and 1 - r % 2: adjacent 64-column slots of an
+# eight-slot ring (slot = output row mod 8), ONE MMA of N = 128 per horizontal tap.  An even input row r completes output row r/2 - 1.
+# ---------------------------------------------------------------------------------------------------------------------
+DOWN_RING_LEAD = 8
+
+
+def down_ring_row_mmas(r, y0, y1):
+    """MMAs input row r issues per horizontal tap for the piece of OUTPUT rows [y0, y1): [(first entry e0, entries, first TMEM column)];
+    entry e = output row (r - 1) // 2 + e, vertical tap ky = 3 - r % 2 - 2 e"""
+    of = (r - 1) // 2
+    runs, run = [], []
+    for e in range(2):
+        o = of + e
+        if not (y0 <= o < y1):
+            if run:
+                runs.append(run)
+            run = []
+            continue
+        c = (o % 8) * 64
+        if run and c == run[-1][1] + 64:
+            run.append((e, c))
+        else:
+            if run:
+                runs.append(run)
+            run = [(e, c)]
+    if run:
+        runs.append(run)
+    return [(rn[0][0], len(rn), rn[0][1]) for rn in runs]
+
+
+def down_ring_weights(w, dtype=torch.bfloat16):
+    """w: Conv2d weight [Cout, 64, 4, 4] -> [Cout/64][4 kx][2 input-row parities][2 entries][64 co][64 ci] as rows of 64"""
+    out = []
+    for g in range(w.shape[0] // 64):
+        for kx in range(4):
+            for par in range(2):
+                for e in range(2):
+                    out.append(w[g * 64:(g + 1) * 64, :, 3 - par - 2 * e, kx])
+    return torch.cat(out, 0).to(dtype).contiguous()
+
+
+def down_ring(x, in_stats, w_stacks, bias, Cout, out=None, co_off=0, stats=None, ci_off=0):
+    """Conv2d(64, Cout, 4, 2, 1) of ReLU(IN(x)) (in_stats: fp64 [N,C,2] raw plane sums of x; None: x is used as it is):
+    x [N,H,W,>=64] bf16 -> out [N,H/2,W/2,Co_total] bf16 (Cout channels at co_off), IN statistics accumulated into stats."""
+    ops._dev(x)
+    N, H, W, Ci_total = x.shape
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, Cout), device=x.device, dtype=torch.bfloat16)
+    rows = (Cout // 64) * 1024
+    if tuple(w_stacks.shape) != (rows, 64) or w_stacks.dtype != torch.bfloat16:
+        raise ValueError(f"down_ring: w_stacks must be bf16 [{rows}, 64] (down_ring_weights), got {tuple(w_stacks.shape)}")
+    d = _lib.DownRingDesc()
+    d.dtype, d.N, d.H, d.W, d.Cout = _lib.BF16, N, H, W, Cout
+    d.Ci_total, d.ci_off, d.Co_total, d.co_off = Ci_total, ci_off, out.shape[3], co_off
+    d.Cs_total, d.cs_off = (in_stats.shape[1], 0) if in_stats is not None else (0, 0)
+    d.flags = _lib.CONV_STATS if stats is not None else 0
+    _lib.call("msg_down_ring", ctypes.byref(d), ops._p(x), ops._p(in_stats), ops._p(w_stacks), ops._p(bias), ops._p(out), ops._p(stats),
+              ops._stream())
+    _lib.launches += Cout // 64 - 1                 # one kernel per 64 output channels
+    return out

@@ -396,3 +396,36 @@ def test_out7_ring_matches_apply_plus_output_conv(N, H, W):
     assert_parity(got, ref32, 1e-2, "out7 ring vs fp32 modules")
     got2 = slab.out7_ring(fh, st, ah, slab.out7_ring_weights(w), bias)
     assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("N,H,W,Cout,fused", [(1, 16, 256, 128, True), (2, 40, 64, 128, True), (1, 10, 20, 64, True), (3, 34, 200, 128, True),
+                                              (2, 64, 512, 128, True), (1, 22, 272, 64, False)])
+def test_down_ring_matches_apply_plus_strided_conv(N, H, W, Cout, fused):
+    """csrc/down_ring.cu: Conv2d(64, Cout, 4, stride 2, padding 1) of ReLU(IN(x)) in one launch per 64 output channels (even / odd pixel
+    slabs normalised in shared memory, the two vertical taps of a horizontal tap as one N = 128 MMA through a ring of TMEM row
+    accumulators) vs the reference's modules (enhanced_generator.py:93-104) on the product apply kernel's bf16 a, with the IN
+    statistics of its epilogue; and without the fused norm."""
+    from multi_style_transfer_gan_b200 import ops, slab
+    torch.manual_seed(N * 1000 + H + W + Cout)
+    x = (torch.randn(N, 64, H, W, device=DEV) * 1.3 - 0.2).bfloat16()
+    w = (torch.randn(Cout, 64, 4, 4, device=DEV) * (2.0 / (64 * 16)) ** 0.5).bfloat16().float()
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    xh = nhwc(x)
+    if fused:
+        sti = ops.instnorm_stats(xh)
+        a = ops.instnorm_apply(xh, sti, ops.ACT_RELU)                      # the product's apply kernel (bf16 out)
+    else:
+        sti, a = None, xh
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), w, bias, stride=2, padding=1)
+    st = ops.new_stats(N, Cout + 64, DEV)
+    out = torch.zeros(N, H // 2, W // 2, Cout + 64, device=DEV, dtype=torch.bfloat16)
+    ws = slab.down_ring_weights(w)
+    slab.down_ring(xh, sti, ws, bias, Cout, out=out, co_off=64, stats=st)
+    torch.cuda.synchronize()
+    assert float(out[..., :64].abs().max()) == 0.0
+    assert_parity(out[..., 64:].float().permute(0, 3, 1, 2), ref, 1e-2, f"down ring {N}x{H}x{W}->{Cout}")
+    assert_parity(st[:, 64:, 0].float(), ref.sum(dim=(2, 3)), 2e-3, "ring sum", floor=1e-2)
+    assert_parity(st[:, 64:, 1].float(), (ref * ref).sum(dim=(2, 3)), 2e-3, "ring sum of squares")
+    out2 = torch.zeros_like(out)
+    slab.down_ring(xh, sti, ws, bias, Cout, out=out2, co_off=64)
+    assert torch.equal(out, out2)

@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-FAMILY = re.compile(r"conv_tma_kernel|conv_slab_kernel|conv_shift_kernel|conv_tc_kernel|msb64_ring_kernel|msb_ring_kernel|convt_ring_kernel|out7_ring_kernel|la_stage_kernel|local_attn_fwd_tc_kernel")
+FAMILY = re.compile(r"conv_tma_kernel|conv_slab_kernel|conv_shift_kernel|conv_tc_kernel|msb64_ring_kernel|msb_ring_kernel|convt_ring_kernel|out7_ring_kernel|down_ring_kernel|la_stage_kernel|local_attn_fwd_tc_kernel")
 
 
 def main():

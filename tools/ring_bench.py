@@ -68,8 +68,29 @@ def bench_out7(N, H, W):
     print(f"apply kernel + taps-as-N conv (2 launches)                : {timed(two):.4f} ms")
 
 
+def bench_down(N, H, W):
+    x = torch.randn(N, H, W, 64, device="cuda").bfloat16()
+    w = torch.randn(128, 64, 4, 4, device="cuda") * 0.03
+    bias = torch.randn(128, device="cuda") * 0.1
+    sti = ops.instnorm_stats(x)
+    st = ops.new_stats(N, 128, "cuda")
+    out = torch.empty(N, H // 2, W // 2, 128, device="cuda", dtype=torch.bfloat16)
+    wr = slab.down_ring_weights(w)
+    print(f"down1 {N}x{H}x{W}: fused ring (IN + ReLU + conv 4x4 s2, 2 launches) : {timed(lambda: slab.down_ring(x, sti, wr, bias, 128, out=out, stats=st)):.4f} ms")
+    print(f"      ring without the fused norm                              : {timed(lambda: slab.down_ring(x, None, wr, bias, 128, out=out, stats=st)):.4f} ms")
+    g = ops.ConvGeom("conv", 64, 128, 4, 2, 1)
+    wp = g.pack_fwd(w, torch.bfloat16)
+    a = torch.empty_like(x)
+
+    def two():
+        ops.instnorm_apply(x, sti, ops.ACT_RELU, out=a)
+        g.forward(a, wp, bias, out=out, stats=st)
+    print(f"      apply kernel + per-tap implicit GEMM (2 launches)        : {timed(two):.4f} ms")
+
+
 def main():
     N, H, W = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (16, 512, 512)
+    bench_down(N, H, W)
     bench_out7(N, H, W)
     bench_convt(N, H // 2, W // 2)
     bench128(N, H // 2, W // 2)
