@@ -166,7 +166,7 @@ def csrc_digest():
     return h.hexdigest()[:16]
 
 
-def measured_traffic(key):
+def measured_traffic(key, micro_batch=None):
     """profiles/traffic.json: {"csrc_sha": ..., "ncu_file": ..., key: bytes per launch}; None when absent or stale."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
@@ -174,6 +174,8 @@ def measured_traffic(key):
     d = json.load(open(p))
     if d.get("csrc_sha") != csrc_digest():
         return None, f"stale: {d.get('ncu_file')} was captured on csrc {d.get('csrc_sha')}, sources are now {csrc_digest()}"
+    if micro_batch is not None and d.get("micro_batch", 16) != micro_batch:
+        return None, f"{d.get('ncu_file')} was captured at micro-batch {d.get('micro_batch', 16)}, this run uses {micro_batch}"
     return d.get(key), f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {d.get('ncu_file')} (csrc {d.get('csrc_sha')})"
 
 
@@ -267,8 +269,8 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
     flops = 3 * B_rank * gflop * scale * 1e9
     if conv_ms > 0:
         ach = flops / (conv_ms * 1e-3) / 1e12
-        traffic, tnote = (measured_traffic("conv_dram_bytes_per_launch") if (H == 512 and args.micro_batch == 16 and args.channels == 64
-                                                                              and B_rank % 16 == 0) else (None, "not the profiled configuration"))
+        traffic, tnote = (measured_traffic("conv_dram_bytes_per_launch", args.micro_batch) if (H == 512 and args.channels == 64
+                                                                              and B_rank % args.micro_batch == 0) else (None, "not the profiled configuration"))
         out["roofline"] = {"bound": "tensor",
                            "kernel": "conv_tma_kernel + conv_slab_kernel + conv_shift_kernel"
                                      + (" + msb_ring_kernel" if (breakdown.get("msg_msb64_ring", {}).get("launches", 0)
@@ -597,7 +599,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--channels", type=int, default=64)
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the embedded train / gram / highres measurements")

@@ -27,7 +27,7 @@ def shard_range(num_images, rank, world_size):
 
 
 class MultiStyleStylizer:
-    def __init__(self, generators, precision="bf16", micro_batch=16, style_streams=None, use_graph=None):
+    def __init__(self, generators, precision="bf16", micro_batch=32, style_streams=None, use_graph=None):
         if not generators:
             raise ValueError("need at least one generator (one per style)")
         self.generators = list(generators)

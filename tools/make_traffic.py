@@ -1,8 +1,8 @@
 """profiles/traffic.json from an ncu launch list of the stylise step that also carries DRAM bytes:
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-        --log-file gpurun_out/stylise_launches.csv python bench.py --batch 16 --steps 1 --warmup 1 --no-extras --no-cpu-baseline
-    python tools/make_traffic.py gpurun_out/stylise_launches.csv profiles/r2_stylise_launch_list.md
+        --log-file gpurun_out/stylise_launches.csv python bench.py --batch 32 --micro-batch 32 --steps 1 --warmup 1 --no-extras --no-cpu-baseline
+    python tools/make_traffic.py gpurun_out/stylise_launches.csv profiles/r2_stylise_launch_list.md 32
 
 The LAST forward (from the last nchw_to_nhwc launch to the last blend) is taken as the sample; the tensor-core family is every
 conv_tma / conv_slab / conv_shift / conv_tc / msb_ring / convt_ring / la_stage / local_attn_fwd_tc launch in it (bench.py's roofline family)."""
@@ -20,6 +20,7 @@ FAMILY = re.compile(r"conv_tma_kernel|conv_slab_kernel|conv_shift_kernel|conv_tc
 
 def main():
     src, out_md = sys.argv[1], sys.argv[2]
+    mb = int(sys.argv[3]) if len(sys.argv) > 3 else 32       # images per forward of the captured run (--batch / --micro-batch)
     lines = [l for l in open(src) if not l.startswith("==")]
     r = list(csv.reader(lines))
     ix = {h: i for i, h in enumerate(r[0])}
@@ -43,7 +44,7 @@ def main():
     fam_bytes = sum(l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0) for l in fam)
     import bench
     tj = {"csrc_sha": bench.csrc_digest(), "ncu_file": os.path.relpath(out_md, ROOT),
-          "conv_dram_bytes_per_launch": fam_bytes / len(fam), "family_launches_per_forward": len(fam),
+          "micro_batch": mb, "conv_dram_bytes_per_launch": fam_bytes / len(fam), "family_launches_per_forward": len(fam),
           "family_share_of_forward_time": fam_ns / tot_ns}
     json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     agg = collections.OrderedDict()
@@ -55,9 +56,9 @@ def main():
         a[1] += 1
         a[2] += l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0)
     with open(out_md, "w") as f:
-        f.write("# ncu launch list of one generator forward (16 images of the 512x512 step, bf16) + blend\n\n")
+        f.write(f"# ncu launch list of one generator forward ({mb} images of the 512x512 step, bf16) + blend\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` on\n"
-                "`python bench.py --batch 16 --steps 1 --warmup 1 --no-extras --no-cpu-baseline`; last forward of the run.\n"
+                f"`python bench.py --batch {mb} --micro-batch {mb} --steps 1 --warmup 1 --no-extras --no-cpu-baseline`; last forward of the run.\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n\n")
         f.write(f"{len(fwd)} launches, {tot_ns / 1e6:.3f} ms summed; tensor-core family: {len(fam)} launches, {fam_ns / 1e6:.3f} ms "
                 f"({100 * fam_ns / tot_ns:.1f} %), DRAM {fam_bytes / 1e9:.3f} GB = {fam_bytes / len(fam) / 1e6:.1f} MB per launch "
