@@ -166,6 +166,17 @@ def csrc_digest():
     return h.hexdigest()[:16]
 
 
+def standalone_apply_elems(per_fwd, c, H, W):
+    """elements moved per image by the stand-alone IN apply launches of one forward.  8 of the 13 applies are always fused into their
+    consumers (no HBM pass).  5 left: the initial IN (1 read + 1 write of [c, H, W]) and the four MultiScaleBlock outputs (read +
+    residual read + write).  3 left (c = 64 inference with the fused down / output ring kernels): the MultiScaleBlock outputs of
+    down1, down2 and up1."""
+    msb3 = 3 * (2 * (2 * c) * (H // 2) * (W // 2) + (4 * c) * (H // 4) * (W // 4))
+    if per_fwd == 3:
+        return msb3
+    return c * H * W * 2 + msb3 + 3 * c * H * W
+
+
 def measured_traffic(key, micro_batch=None):
     """profiles/traffic.json: {"csrc_sha": ..., "ncu_file": ..., key: bytes per launch}; None when absent or stale."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -296,11 +307,8 @@ def roofline_blocks(args, B_rank, breakdown, ms_serial, pk):
         per_fwd = in_launches // (3 * max(1, (B_rank + args.micro_batch - 1) // args.micro_batch))
         c = args.channels
         if per_fwd <= 5:
-            # 8 of the 13 IN applies of a forward are fused into their consumers (no HBM pass at all); the stand-alone
-            # launches left are the initial IN (1 read + 1 write of [c, H, W]) and the four MultiScaleBlock outputs
-            # (read + residual read + write): bytes of exactly those launches (bf16)
-            elems = c * H * W * 2 + 3 * (2 * (2 * c) * (H // 2) * (W // 2) + (4 * c) * (H // 4) * (W // 4) + c * H * W)
-            in_bytes, note = elems * 2, f"{per_fwd} stand-alone apply launches per forward (the others are fused into their consumers)"
+            in_bytes = standalone_apply_elems(per_fwd, c, H, W) * 2
+            note = f"{per_fwd} stand-alone apply launches per forward (the others are fused into their consumers)"
         else:
             in_bytes, note = IN_BYTES_512_BF16 * scale, "13 apply launches per forward, 1 read + 1 write each (SURVEY 8d)"
         gbs = 3 * B_rank * in_bytes / (in_ms * 1e-3) / 1e9
@@ -470,8 +478,7 @@ def bench_highres(cx, args):
         per_fwd = n // (4 * 2)
         H = W = 1024
         c = 64
-        elems = c * H * W * 2 + 3 * (2 * (2 * c) * (H // 2) * (W // 2) + (4 * c) * (H // 4) * (W // 4) + c * H * W) if per_fwd <= 5 \
-            else IN_BYTES_512_BF16 * 4 / 2
+        elems = standalone_apply_elems(per_fwd, c, H, W) if per_fwd <= 5 else IN_BYTES_512_BF16 * 4 / 2
         gbs = 4 * 8 * elems * 2 / (in_ms * 1e-3) / 1e9
         out["instnorm"] = {"gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "ms": in_ms, "standalone_apply_launches_per_forward": per_fwd}
     del gens, st, ser
