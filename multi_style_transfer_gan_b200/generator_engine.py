@@ -93,13 +93,21 @@ class GeneratorEngine:
         self._cache = {}
         # row-slab programs (bf16 path, widths that are multiples of 64): fused MSB branches, 7x7 convs
         self.use_slab = True
-        self._msb_prog = {C: slab.msb_program(C) for C in set(self.width.values()) if C % 64 == 0}
-        self._msb_dprog = {C: slab.msb_dgrad_program(C) for C in set(self.width.values()) if C % 64 == 0}
-        self._in_prog = slab.conv7_in_program(c) if c % 16 == 0 else None
-        self._out_prog = slab.conv7_out_shift_program(c) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
+        def fits(build):
+            # a program that exceeds the descriptor's tap / K-block tables (wide generators: C = 512 at c = 128) is simply not
+            # offered: those layers take the per-tap TMA kernel
+            try:
+                return build()
+            except ValueError:
+                return None
+        widths = sorted(C for C in set(self.width.values()) if C % 64 == 0)
+        self._msb_prog = {C: pr for C in widths for pr in [fits(lambda: slab.msb_program(C))] if pr is not None}
+        self._msb_dprog = {C: pr for C in widths for pr in [fits(lambda: slab.msb_dgrad_program(C))] if pr is not None}
+        self._in_prog = fits(lambda: slab.conv7_in_program(c)) if c % 16 == 0 else None
+        self._out_prog = fits(lambda: slab.conv7_out_shift_program(c)) if c % 64 == 0 else None     # taps-as-N (conv_shift.cu)
         self._msb64_prog = slab.msb64_shift_program()
-        self._convT_prog = {s: slab.convT_phase_programs(self.inwidth[s], self.width[s]) for s in ("up1", "up2")
-                            if self.inwidth[s] % 64 == 0 and self.width[s] % 16 == 0}
+        self._convT_prog = {s: pr for s in ("up1", "up2") if self.inwidth[s] % 64 == 0 and self.width[s] % 16 == 0
+                            for pr in [fits(lambda: slab.convT_phase_programs(self.inwidth[s], self.width[s]))] if pr is not None}
         self.convT_slab = os.environ.get("MSG_CONVT_SLAB", "1") == "1"
         self.msb64_taps_as_n = os.environ.get("MSG_MSB64_SHIFT", "0") == "1"
         # Row-ring kernel for the C = 64 branches (csrc/msb_ring.cu): 0.48 ms per 16 images at 512^2 vs 0.67 ms for the per-tap slab
@@ -196,7 +204,7 @@ class GeneratorEngine:
             wsl = self._slab_cached(P, (s, "convT_ring_w"), [wn], lambda: slab.convt_ring_weights(P[wn].detach()))
             y0 = torch.empty((N, 2 * a_in.shape[1], 2 * a_in.shape[2], C), device=dev, dtype=dtype)
             slab.convt_ring(a_in, wsl, self._bias(P, f"{s}.0"), C, out=y0, stats=st0)
-        elif (self.convT_slab and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
+        elif (self.convT_slab and s in self._convT_prog and g[f"{s}.0"].kind == "convT" and dtype == torch.bfloat16 and self.inwidth[s] % 64 == 0 and
                 C % 16 == 0 and C * self.inwidth[s] <= 64 * 128 and a_in.shape[2] % 8 == 0):
             # (weights of a phase resident in shared memory: 128 -> 64 measured 0.64 -> 0.49 ms per 16 images at 256^2;
             #  with streamed weights, 256 -> 128, the per-tap TMA kernel is as fast: 0.36 vs 0.38 ms)

@@ -478,17 +478,19 @@ def test_pretrain_generator_bf16_and_step(golden):
     assert losses[-1] < losses[0], losses
 
 
-def test_c64_fused_ring_inference_matches_the_unfused_engine_paths():
+@pytest.mark.parametrize("c", [64, 32, 128])
+def test_ring_inference_matches_the_unfused_engine_paths(c):
     """Inference at c = 64 (bf16) with the row-ring kernels and their fused InstanceNorm applies (csrc/msb_ring.cu, convt_ring.cu,
     down_ring.cu, out7_ring.cu) vs the same generator on the per-tap kernels + stand-alone apply launches, both measured against the
     fp32 engine (enhanced_generator.py:86-147): two bf16 evaluations of a 60-layer network differ from each other by as much as each
     differs from fp32, so the gate is that the ring path is no further from fp32 than the per-tap path; on a plane narrower than a
-    strip and on one with several strips."""
+    strip and on one with several strips.  c = 32 / 128 put the MultiScaleBlock and transposed-conv rings on other stages (the fused
+    down / output kernels are c = 64 only)."""
     from multi_style_transfer_gan_b200.enhanced_generator import EnhancedGenerator
     torch.manual_seed(11)
-    G = EnhancedGenerator(channels=64, num_transformer_blocks=1).to(DEV).eval()
+    G = EnhancedGenerator(channels=c, num_transformer_blocks=1).to(DEV).eval()
     eng = G._engine
-    for H, W in ((64, 64), (32, 1040)):
+    for H, W in ((64, 64), (32, 1040)) if c == 64 else ((48, 272),):
         x = torch.rand(2, 3, H, W, device=DEV) * 2 - 1
         with torch.no_grad():
             y32 = G.set_precision("fp32")(x).float().clone()
@@ -505,4 +507,4 @@ def test_c64_fused_ring_inference_matches_the_unfused_engine_paths():
         assert torch.isfinite(y_ring).all()
         e_ring = float((y_ring - y32).norm() / y32.norm())
         e_tap = float((y_tap - y32).norm() / y32.norm())
-        assert e_ring <= 1.25 * e_tap + 1e-3, (H, W, e_ring, e_tap)
+        assert e_ring <= 1.25 * e_tap + 1e-3, (c, H, W, e_ring, e_tap)
