@@ -68,3 +68,48 @@ def test_state_dict_contract():
         inner = wrap.get("G_AB_state_dict", wrap.get("model_state_dict", wrap))
         EnhancedGenerator(16, 1).load_state_dict(inner, strict=True)
     assert hasattr(G, "gradient_checkpointing_enable")
+
+
+STRUCTS = {"msg_conv_desc": "ConvDesc", "msg_slab_desc": "SlabDesc", "msg_shift_desc": "ShiftDesc", "msg_msb_ring_desc": "MsbRingDesc",
+           "msg_convt_ring_desc": "ConvtRingDesc", "msg_out7_ring_desc": "Out7RingDesc", "msg_down_ring_desc": "DownRingDesc",
+           "msg_sn_batch": "SnBatch"}
+
+
+def test_every_descriptor_struct_matches_its_ctypes_mirror(tmp_path):
+    """include/msg_b200.h is plain C: a C compiler's sizeof / offsetof of every descriptor struct and field equals the ctypes
+    Structure the Python host binds with (a reordered or missing field would silently shift every argument behind it)."""
+    import subprocess
+    from multi_style_transfer_gan_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "msg_b200.h")).read()
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "msg_b200.h")}"', "int main(void) {"]
+    fields = {}
+    for cname, pyname in STRUCTS.items():
+        end = hdr.index("} " + cname + ";")
+        start = hdr.rfind("typedef struct {", 0, end)
+        assert start >= 0, cname
+        body = re.sub(r"/\*.*?\*/", "", hdr[start + len("typedef struct {"):end], flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(unsigned\s+int|unsigned\s+char|unsigned|long\s+long|int|float|double|void|u?int\d+_t|size_t|char)\b\s*\**\s*",
+                          "", decl, count=1)      # drop the type
+            names += [re.sub(r"\[.*?\]", "", n).replace("*", "").strip() for n in decl.split(",")]
+        fields[cname] = names
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for n in names:
+            src.append(f'  printf("{cname}.{n} %zu\\n", offsetof({cname}, {n}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(c)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, pyname in STRUCTS.items():
+        cls = getattr(_lib, pyname)
+        assert ctypes.sizeof(cls) == int(out[cname]), (cname, ctypes.sizeof(cls), out[cname])
+        py_fields = [f[0] for f in cls._fields_]
+        assert py_fields == fields[cname], (cname, py_fields, fields[cname])
+        for n in py_fields:
+            assert getattr(cls, n).offset == int(out[f"{cname}.{n}"]), (cname, n)
